@@ -1,0 +1,326 @@
+// attention.cu — exact softmax attention over each graph's own node set, without densification.
+//
+// Replaces to_dense_batch -> nn.MultiheadAttention core -> [mask] of the reference
+// (graphgps/layer/gps_layer.py:199-201, 234-241): the padded [B,Nmax,d] tensor, the key-padding
+// mask and the boolean-mask gather (two host syncs per layer) disappear; every query row attends to
+// the rows [graph_ptr[g], graph_ptr[g+1]) of its own graph directly in the packed [N, *] layout.
+//
+// Mapping (CUDA-core version; the flop share of this stage is <1% of the layer at the PCQM/ZINC
+// shapes, 4*d*sum n_g^2 vs 24*N*d^2 — SURVEY.md 8d): query rows are packed densely into warps
+// regardless of graph boundaries; LPR lanes cooperate on one row, each holding CH float4 chunks
+// of the head dimension, so q/o (fwd) and k/v/dk/dv (bwd) live in registers and a dot product is
+// an LPR-lane shuffle reduction.  Online softmax in fp32; dropout on the probabilities uses the
+// Philox stream (site GPS_SITE_ATTN_P + head).
+// Backward = two passes (query-major for dQ and delta, key-major for dK, dV): no atomics.
+#include "kernels.cuh"
+
+namespace gps {
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+
+__device__ __forceinline__ int find_graph(const int* __restrict__ gptr, int B, int node) {
+  // largest g with gptr[g] <= node  (graphs may be empty)
+  int lo = 0, hi = B;  // invariant: gptr[lo] <= node < gptr[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (gptr[mid] <= node) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ int warp_max_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float drop_scale_pair(float p, uint64_t seed, uint64_t offset, int head, int i, int jl) {
+  if (p <= 0.f) return 1.f;
+  Philox4 r = philox4x32(seed, offset + (uint64_t)(GPS_SITE_ATTN_P + head), ((uint64_t)i << 20) | (uint64_t)(jl >> 2));
+  uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
+  return r.v[jl & 3] >= thr ? 1.f / (1.f - p) : 0.f;
+}
+
+// lane-slice helpers: lane `sub` of a row group owns float4 chunks sub, sub+LPR, ... (< nch)
+template <int CH, int LPR>
+__device__ __forceinline__ void load_slice(float4* dst, const float* row, int sub, int nch, bool ok) {
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    int ch = sub + c * LPR;
+    dst[c] = (ok && ch < nch) ? ld4(row + ch * 4) : f4zero();
+  }
+}
+template <int CH, int LPR>
+__device__ __forceinline__ void store_slice(const float4* src, float* row, int sub, int nch) {
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    int ch = sub + c * LPR;
+    if (ch < nch) st4(row + ch * 4, src[c]);
+  }
+}
+template <int CH>
+__device__ __forceinline__ float dot_slice(const float4* a, const float4* b) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) s += a[c].x * b[c].x + a[c].y * b[c].y + a[c].z * b[c].z + a[c].w * b[c].w;
+  return s;
+}
+
+struct AttnArgs {
+  const int* gptr; int B; int N; int H; int hd;
+  const float* Q; const float* K; const float* V; int64_t ld;
+  float* O; const float* Oc; const float* dO; int64_t ldo;
+  float* lse; const float* lsec; float* delta; const float* deltac;
+  float* dQ; float* dK; float* dV; int64_t ldg;
+  float scale; float p_drop; uint64_t seed, offset;
+};
+
+template <int CH, int LPR>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_fwd(AttnArgs a) {
+  constexpr int RPW = 32 / LPR;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane % LPR, rloc = lane / LPR;
+  const int h = blockIdx.y;
+  const int i = (blockIdx.x * kWarpsPerBlock + warp) * RPW + rloc;
+  const bool row_ok = i < a.N;
+  const int nch = a.hd / 4;
+  int gs = 0, n = 0;
+  if (row_ok) {
+    int g = find_graph(a.gptr, a.B, i);
+    gs = a.gptr[g];
+    n = a.gptr[g + 1] - gs;
+  }
+  const int nloop = warp_max_i(n);
+  const int64_t hoff = (int64_t)h * a.hd;
+  float4 q[CH], o[CH];
+  load_slice<CH, LPR>(q, a.Q + (int64_t)(row_ok ? i : 0) * a.ld + hoff, sub, nch, row_ok);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    q[c] = f4scale(q[c], a.scale);
+    o[c] = f4zero();
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int jl = 0; jl < nloop; ++jl) {
+    const bool valid = jl < n;
+    const int j = gs + (valid ? jl : 0);
+    float4 kv[CH];
+    load_slice<CH, LPR>(kv, a.K + (int64_t)j * a.ld + hoff, sub, nch, valid);
+    float s = group_sum<LPR>(dot_slice<CH>(q, kv));
+    s = valid ? s : -INFINITY;
+    const float m_new = fmaxf(m, s);
+    const float corr = (m_new == -INFINITY) ? 1.f : __expf(m - m_new);
+    const float p = valid ? __expf(s - m_new) : 0.f;
+    l = l * corr + p;
+    const float pd = p * drop_scale_pair(a.p_drop, a.seed, a.offset, h, i, jl);
+    load_slice<CH, LPR>(kv, a.V + (int64_t)j * a.ld + hoff, sub, nch, valid);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      o[c].x = o[c].x * corr + pd * kv[c].x;
+      o[c].y = o[c].y * corr + pd * kv[c].y;
+      o[c].z = o[c].z * corr + pd * kv[c].z;
+      o[c].w = o[c].w * corr + pd * kv[c].w;
+    }
+    m = m_new;
+  }
+  if (row_ok) {
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) o[c] = f4scale(o[c], inv);
+    store_slice<CH, LPR>(o, a.O + (int64_t)i * a.ldo + hoff, sub, nch);
+    if (sub == 0) a.lse[(int64_t)i * a.H + h] = m + __logf(l);
+  }
+}
+
+// query-major backward: dQ_i and delta_i = dO_i . O_i
+template <int CH, int LPR>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_q(AttnArgs a) {
+  constexpr int RPW = 32 / LPR;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane % LPR, rloc = lane / LPR;
+  const int h = blockIdx.y;
+  const int i = (blockIdx.x * kWarpsPerBlock + warp) * RPW + rloc;
+  const bool row_ok = i < a.N;
+  const int nch = a.hd / 4;
+  int gs = 0, n = 0;
+  if (row_ok) {
+    int g = find_graph(a.gptr, a.B, i);
+    gs = a.gptr[g];
+    n = a.gptr[g + 1] - gs;
+  }
+  const int nloop = warp_max_i(n);
+  const int64_t hoff = (int64_t)h * a.hd;
+  const int ir = row_ok ? i : 0;
+  float4 q[CH], go[CH], gq[CH];
+  load_slice<CH, LPR>(q, a.Q + (int64_t)ir * a.ld + hoff, sub, nch, row_ok);
+  load_slice<CH, LPR>(go, a.dO + (int64_t)ir * a.ldo + hoff, sub, nch, row_ok);
+  {
+    float4 oo[CH];
+    load_slice<CH, LPR>(oo, a.Oc + (int64_t)ir * a.ldo + hoff, sub, nch, row_ok);
+    float dl = group_sum<LPR>(dot_slice<CH>(go, oo));
+    if (row_ok && sub == 0) a.delta[(int64_t)i * a.H + h] = dl;
+    // keep in register via q-scaling trick below
+#pragma unroll
+    for (int c = 0; c < CH; ++c) gq[c] = f4zero();
+    const float lse = row_ok ? a.lsec[(int64_t)i * a.H + h] : 0.f;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) q[c] = f4scale(q[c], a.scale);
+    for (int jl = 0; jl < nloop; ++jl) {
+      const bool valid = jl < n;
+      const int j = gs + (valid ? jl : 0);
+      float4 kk[CH], vv[CH];
+      load_slice<CH, LPR>(kk, a.K + (int64_t)j * a.ld + hoff, sub, nch, valid);
+      load_slice<CH, LPR>(vv, a.V + (int64_t)j * a.ld + hoff, sub, nch, valid);
+      float s = dot_slice<CH>(q, kk), dp = dot_slice<CH>(go, vv);
+#pragma unroll
+      for (int ofs = LPR / 2; ofs > 0; ofs >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, ofs);
+        dp += __shfl_xor_sync(0xffffffffu, dp, ofs);
+      }
+      const float p = valid ? __expf(s - lse) : 0.f;
+      const float ds = p * (dp * drop_scale_pair(a.p_drop, a.seed, a.offset, h, i, jl) - dl);
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        gq[c].x += ds * kk[c].x;
+        gq[c].y += ds * kk[c].y;
+        gq[c].z += ds * kk[c].z;
+        gq[c].w += ds * kk[c].w;
+      }
+    }
+  }
+  if (row_ok) {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) gq[c] = f4scale(gq[c], a.scale);
+    store_slice<CH, LPR>(gq, a.dQ + (int64_t)i * a.ldg + hoff, sub, nch);
+  }
+}
+
+// key-major backward: dK_j, dV_j
+template <int CH, int LPR>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_kv(AttnArgs a) {
+  constexpr int RPW = 32 / LPR;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane % LPR, rloc = lane / LPR;
+  const int h = blockIdx.y;
+  const int j = (blockIdx.x * kWarpsPerBlock + warp) * RPW + rloc;
+  const bool row_ok = j < a.N;
+  const int nch = a.hd / 4;
+  int gs = 0, n = 0;
+  if (row_ok) {
+    int g = find_graph(a.gptr, a.B, j);
+    gs = a.gptr[g];
+    n = a.gptr[g + 1] - gs;
+  }
+  const int nloop = warp_max_i(n);
+  const int jl = j - gs;
+  const int64_t hoff = (int64_t)h * a.hd;
+  const int jr = row_ok ? j : 0;
+  float4 kk[CH], vv[CH], gk[CH], gv[CH];
+  load_slice<CH, LPR>(kk, a.K + (int64_t)jr * a.ld + hoff, sub, nch, row_ok);
+  load_slice<CH, LPR>(vv, a.V + (int64_t)jr * a.ld + hoff, sub, nch, row_ok);
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    gk[c] = f4zero();
+    gv[c] = f4zero();
+  }
+  for (int il = 0; il < nloop; ++il) {
+    const bool valid = il < n;
+    const int i = gs + (valid ? il : 0);
+    float4 q[CH], go[CH];
+    load_slice<CH, LPR>(q, a.Q + (int64_t)i * a.ld + hoff, sub, nch, valid);
+    load_slice<CH, LPR>(go, a.dO + (int64_t)i * a.ldo + hoff, sub, nch, valid);
+    float s = dot_slice<CH>(q, kk), dp = dot_slice<CH>(go, vv);
+#pragma unroll
+    for (int ofs = LPR / 2; ofs > 0; ofs >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, ofs);
+      dp += __shfl_xor_sync(0xffffffffu, dp, ofs);
+    }
+    const float lse = valid ? a.lsec[(int64_t)i * a.H + h] : 0.f;
+    const float dl = valid ? a.deltac[(int64_t)i * a.H + h] : 0.f;
+    const float p = valid ? __expf(s * a.scale - lse) : 0.f;
+    const float dsc = drop_scale_pair(a.p_drop, a.seed, a.offset, h, i, jl);
+    const float pd = p * dsc;
+    const float ds = p * (dp * dsc - dl) * a.scale;
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      gk[c].x += ds * q[c].x; gk[c].y += ds * q[c].y; gk[c].z += ds * q[c].z; gk[c].w += ds * q[c].w;
+      gv[c].x += pd * go[c].x; gv[c].y += pd * go[c].y; gv[c].z += pd * go[c].z; gv[c].w += pd * go[c].w;
+    }
+  }
+  if (row_ok) {
+    store_slice<CH, LPR>(gk, a.dK + (int64_t)j * a.ldg + hoff, sub, nch);
+    store_slice<CH, LPR>(gv, a.dV + (int64_t)j * a.ldg + hoff, sub, nch);
+  }
+}
+
+enum { KFWD = 0, KBWDQ = 1, KBWDKV = 2 };
+
+template <int CH, int LPR>
+static void launch_one(int which, const AttnArgs& a, cudaStream_t stream) {
+  constexpr int RPW = 32 / LPR;
+  dim3 grid((unsigned)ceil_div(a.N, (int64_t)RPW * kWarpsPerBlock), (unsigned)a.H, 1);
+  dim3 block(kWarpsPerBlock * 32);
+  if (which == KFWD) k_attn_fwd<CH, LPR><<<grid, block, 0, stream>>>(a);
+  else if (which == KBWDQ) k_attn_bwd_q<CH, LPR><<<grid, block, 0, stream>>>(a);
+  else k_attn_bwd_kv<CH, LPR><<<grid, block, 0, stream>>>(a);
+}
+
+static int dispatch(int which, const AttnArgs& a, cudaStream_t stream) {
+  GPS_REQUIRE(a.hd > 0 && a.hd % 4 == 0, GPS_ERR_UNSUPPORTED, "attention: head dim %d must be a multiple of 4", a.hd);
+  GPS_REQUIRE(a.ld % 4 == 0 && a.ldo % 4 == 0 && (which == KFWD || a.ldg % 4 == 0), GPS_ERR_UNSUPPORTED,
+              "attention: leading dimensions must be multiples of 4");
+  const int nch = a.hd / 4;
+  GPS_REQUIRE(nch <= 48, GPS_ERR_UNSUPPORTED, "attention: head dim %d > 192 not supported", a.hd);
+  if (a.N == 0) return GPS_OK;
+  // smallest power-of-two lane group with <= 6 float4 chunks per lane
+  int lpr = 1;
+  while ((nch + lpr - 1) / lpr > 6) lpr *= 2;
+  const int ch = (nch + lpr - 1) / lpr;
+#define GPS_ATTN_CASE(CHV, LPRV)                                  \
+  if (ch == CHV && lpr == LPRV) {                                 \
+    launch_one<CHV, LPRV>(which, a, stream);                      \
+    GPS_LAUNCH_CHECK();                                           \
+    return GPS_OK;                                                \
+  }
+  GPS_ATTN_CASE(1, 1) GPS_ATTN_CASE(2, 1) GPS_ATTN_CASE(3, 1) GPS_ATTN_CASE(4, 1) GPS_ATTN_CASE(5, 1)
+  GPS_ATTN_CASE(6, 1) GPS_ATTN_CASE(4, 2) GPS_ATTN_CASE(5, 2) GPS_ATTN_CASE(6, 2) GPS_ATTN_CASE(4, 4)
+  GPS_ATTN_CASE(5, 4) GPS_ATTN_CASE(6, 4) GPS_ATTN_CASE(4, 8) GPS_ATTN_CASE(5, 8) GPS_ATTN_CASE(6, 8)
+#undef GPS_ATTN_CASE
+  set_error("attention: no kernel for head dim %d", a.hd);
+  return GPS_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+int attention_fwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, const float* K, const float* V,
+                  int64_t ld, float* O, int64_t ldo, float* lse, float p_drop, uint64_t seed, uint64_t offset,
+                  cudaStream_t stream) {
+  AttnArgs a{};
+  a.gptr = g.graph_ptr; a.B = (int)g.B; a.N = (int)g.N; a.H = (int)heads; a.hd = (int)hd;
+  a.Q = Q; a.K = K; a.V = V; a.ld = ld; a.O = O; a.ldo = ldo; a.lse = lse;
+  a.scale = 1.f / sqrtf((float)hd); a.p_drop = p_drop; a.seed = seed; a.offset = offset;
+  return dispatch(KFWD, a, stream);
+}
+
+int attention_bwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, const float* K, const float* V,
+                  int64_t ld, const float* O, const float* dO, int64_t ldo, const float* lse, float* delta,
+                  float* dQ, float* dK, float* dV, int64_t ldg, float p_drop, uint64_t seed, uint64_t offset,
+                  cudaStream_t stream) {
+  AttnArgs a{};
+  a.gptr = g.graph_ptr; a.B = (int)g.B; a.N = (int)g.N; a.H = (int)heads; a.hd = (int)hd;
+  a.Q = Q; a.K = K; a.V = V; a.ld = ld; a.Oc = O; a.dO = dO; a.ldo = ldo; a.lsec = lse;
+  a.delta = delta; a.deltac = delta; a.dQ = dQ; a.dK = dK; a.dV = dV; a.ldg = ldg;
+  a.scale = 1.f / sqrtf((float)hd); a.p_drop = p_drop; a.seed = seed; a.offset = offset;
+  GPS_TRY(dispatch(KBWDQ, a, stream));
+  return dispatch(KBWDKV, a, stream);
+}
+
+}  // namespace gps

@@ -1,0 +1,308 @@
+// elementwise.cu — row-wise stages of the GPS layer: BatchNorm apply / statistics / backward,
+// residual adds, activation, dropout (gps_layer.py:188-194,212-217,222-229; gatedgcn_layer.py:72-83).
+//
+// One skeleton (k_rowwise): a thread owns one float4 column group and strides over rows, so the
+// per-column BatchNorm constants live in registers and the column statistics are reduced
+// per-thread -> per-CTA (shared memory) -> global (double atomics).  All loads/stores are 128-bit.
+#include "kernels.cuh"
+
+namespace gps {
+
+namespace {
+
+struct RowGeom {
+  dim3 block, grid;
+  size_t smem;
+};
+
+static int row_geom(int64_t rows, int64_t d, int nstat, RowGeom* g) {
+  GPS_REQUIRE(d > 0 && d % 4 == 0 && d / 4 <= 1024, GPS_ERR_UNSUPPORTED,
+              "row-wise stage needs d %% 4 == 0 and d <= 4096 (got %lld)", (long long)d);
+  int C4 = (int)(d / 4);
+  int RY = C4 >= 256 ? 1 : 256 / C4;
+  int64_t blocks = ceil_div(rows > 0 ? rows : 1, (int64_t)RY * 4);
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  g->block = dim3(C4, RY, 1);
+  g->grid = dim3((unsigned)blocks, 1, 1);
+  g->smem = RY > 1 ? (size_t)nstat * RY * C4 * sizeof(float4) : 0;
+  return GPS_OK;
+}
+
+template <class Op>
+__global__ void k_rowwise(Op op, int64_t rows) {
+  extern __shared__ float4 sm[];
+  const int c4 = threadIdx.x, ry = threadIdx.y, RY = blockDim.y, C4 = blockDim.x;
+  constexpr int NS = Op::NS;
+  float4 acc[NS > 0 ? NS : 1];
+#pragma unroll
+  for (int s = 0; s < (NS > 0 ? NS : 1); ++s) acc[s] = f4zero();
+  op.prepare(c4);
+  for (int64_t r = (int64_t)blockIdx.x * RY + ry; r < rows; r += (int64_t)gridDim.x * RY) op.row(r, c4, acc);
+  if (NS > 0) {
+    if (RY > 1) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) sm[(s * RY + ry) * C4 + c4] = acc[s];
+      __syncthreads();
+      if (ry == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s)
+          for (int y = 1; y < RY; ++y) acc[s] = f4add(acc[s], sm[(s * RY + y) * C4 + c4]);
+      }
+    }
+    if (ry == 0) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        double* p = op.stat_ptr(s);
+        if (p) {
+          atomic_add_f64(p + c4 * 4 + 0, (double)acc[s].x);
+          atomic_add_f64(p + c4 * 4 + 1, (double)acc[s].y);
+          atomic_add_f64(p + c4 * 4 + 2, (double)acc[s].z);
+          atomic_add_f64(p + c4 * 4 + 3, (double)acc[s].w);
+        }
+      }
+    }
+  }
+  op.finish(c4, ry);
+}
+
+struct BnRegs {  // per-thread column constants: y = z * sc + sh ; zhat = (z - mean) * invstd
+  float4 mean, invstd, gamma, beta;
+  __device__ void load(const BnView& v, int c4) {
+    mean = ld4(v.mean + c4 * 4);
+    invstd = ld4(v.invstd + c4 * 4);
+    gamma = ld4(v.gamma + c4 * 4);
+    beta = ld4(v.beta + c4 * 4);
+  }
+  __device__ float4 zhat(float4 z) const {
+    return make_float4((z.x - mean.x) * invstd.x, (z.y - mean.y) * invstd.y, (z.z - mean.z) * invstd.z,
+                       (z.w - mean.w) * invstd.w);
+  }
+  __device__ float4 apply(float4 z) const { return f4fma(zhat(z), gamma, beta); }
+};
+
+__device__ __forceinline__ float4 act4(int act, float4 v) {
+  if (act < 0) return v;
+  return make_float4(act_fwd_rt(act, v.x), act_fwd_rt(act, v.y), act_fwd_rt(act, v.z), act_fwd_rt(act, v.w));
+}
+__device__ __forceinline__ float4 dact4(int act, float4 v) {
+  return make_float4(act_bwd_rt(act, v.x), act_bwd_rt(act, v.y), act_bwd_rt(act, v.z), act_bwd_rt(act, v.w));
+}
+
+// ---------------------------------------------------------------- forward: R + drop(act(BN(z)))
+template <bool STATS>
+struct OpBnActRes {
+  static constexpr int NS = STATS ? 2 : 0;
+  const float* z; int64_t ldz;
+  const float* R; float* out; int64_t d;
+  BnView bn; int act; DropCfg drop; double* stats;
+  BnRegs reg;
+  __device__ void prepare(int c4) { reg.load(bn, c4); }
+  __device__ void row(int64_t r, int c4, float4* acc) {
+    float4 v = act4(act, reg.apply(ld4(z + r * ldz + c4 * 4)));
+    if (drop.p > 0.f)
+      v = f4mul(v, dropout_scale4(drop.p, drop.seed, drop.offset, drop.site, (uint64_t)r * (d >> 2) + c4));
+    if (R) v = f4add(v, ld4(R + r * d + c4 * 4));
+    st4(out + r * d + c4 * 4, v);
+    if (STATS) {
+      acc[0] = f4add(acc[0], v);
+      acc[1] = f4fma(v, v, acc[1]);
+    }
+  }
+  __device__ double* stat_ptr(int s) { return stats ? stats + (int64_t)s * d : nullptr; }
+  __device__ void finish(int, int) {}
+};
+
+// ---------------------------------------------------------------- forward: BN(a) [+ BN(b)]
+struct OpCombine {
+  static constexpr int NS = 0;
+  const float* a; const float* b; float* out; int64_t d;
+  BnView bna, bnb;
+  BnRegs ra, rb;
+  __device__ void prepare(int c4) {
+    ra.load(bna, c4);
+    if (b) rb.load(bnb, c4);
+  }
+  __device__ void row(int64_t r, int c4, float4*) {
+    float4 v = ra.apply(ld4(a + r * d + c4 * 4));
+    if (b) v = f4add(v, rb.apply(ld4(b + r * d + c4 * 4)));
+    st4(out + r * d + c4 * 4, v);
+  }
+  __device__ double* stat_ptr(int) { return nullptr; }
+  __device__ void finish(int, int) {}
+};
+
+// ---------------------------------------------------------------- backward of BatchNorm (+act, +dropout)
+__device__ __forceinline__ float4 bn_bwd_gprime(const float* g, int64_t ldg, int64_t r, int c4, float4 zh,
+                                                const BnRegs& reg, int act, const DropCfg& drop, int64_t d) {
+  float4 gp = ld4(g + r * ldg + c4 * 4);
+  if (drop.p > 0.f)
+    gp = f4mul(gp, dropout_scale4(drop.p, drop.seed, drop.offset, drop.site, (uint64_t)r * (d >> 2) + c4));
+  if (act >= 0) gp = f4mul(gp, dact4(act, f4fma(zh, reg.gamma, reg.beta)));
+  return gp;
+}
+
+struct OpBnBwdReduce {
+  static constexpr int NS = 2;
+  const float* g; int64_t ldg; const float* z; int64_t ldz; int64_t d;
+  BnView bn; int act; DropCfg drop; double* sums;
+  BnRegs reg;
+  __device__ void prepare(int c4) { reg.load(bn, c4); }
+  __device__ void row(int64_t r, int c4, float4* acc) {
+    float4 zh = reg.zhat(ld4(z + r * ldz + c4 * 4));
+    float4 gp = bn_bwd_gprime(g, ldg, r, c4, zh, reg, act, drop, d);
+    acc[0] = f4add(acc[0], gp);
+    acc[1] = f4fma(gp, zh, acc[1]);
+  }
+  __device__ double* stat_ptr(int s) { return sums + (int64_t)s * d; }
+  __device__ void finish(int, int) {}
+};
+
+struct OpBnBwdApply {
+  static constexpr int NS = 0;
+  const float* g; int64_t ldg; const float* z; int64_t ldz; int64_t d;
+  BnView bn; int act; DropCfg drop; const double* sums; float inv_n;
+  float* out; int64_t ldo; float* grad_gamma; float* grad_beta;
+  BnRegs reg;
+  float4 m1, m2, gs;  // S1/n, S2/n, gamma*invstd
+  float4 s1raw, s2raw;
+  __device__ void prepare(int c4) {
+    reg.load(bn, c4);
+    const double* a = sums + c4 * 4;
+    const double* b = sums + d + c4 * 4;
+    s1raw = make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);
+    s2raw = make_float4((float)b[0], (float)b[1], (float)b[2], (float)b[3]);
+    m1 = f4scale(s1raw, inv_n);
+    m2 = f4scale(s2raw, inv_n);
+    gs = f4mul(reg.gamma, reg.invstd);
+  }
+  __device__ void row(int64_t r, int c4, float4*) {
+    float4 zh = reg.zhat(ld4(z + r * ldz + c4 * 4));
+    float4 gp = bn_bwd_gprime(g, ldg, r, c4, zh, reg, act, drop, d);
+    float4 v = make_float4(gs.x * (gp.x - m1.x - zh.x * m2.x), gs.y * (gp.y - m1.y - zh.y * m2.y),
+                           gs.z * (gp.z - m1.z - zh.z * m2.z), gs.w * (gp.w - m1.w - zh.w * m2.w));
+    st4(out + r * ldo + c4 * 4, v);
+  }
+  __device__ double* stat_ptr(int) { return nullptr; }
+  __device__ void finish(int c4, int ry) {
+    if (blockIdx.x == 0 && ry == 0) {
+      if (grad_gamma) st4(grad_gamma + c4 * 4, s2raw);
+      if (grad_beta) st4(grad_beta + c4 * 4, s1raw);
+    }
+  }
+};
+
+struct OpAdd3 {
+  static constexpr int NS = 0;
+  const float* a; int64_t lda; const float* b; int64_t ldb; const float* c; int64_t ldc;
+  float* out; int64_t ldo;
+  __device__ void prepare(int) {}
+  __device__ void row(int64_t r, int c4, float4*) {
+    float4 v = ld4(a + r * lda + c4 * 4);
+    if (b) v = f4add(v, ld4(b + r * ldb + c4 * 4));
+    if (c) v = f4add(v, ld4(c + r * ldc + c4 * 4));
+    st4(out + r * ldo + c4 * 4, v);
+  }
+  __device__ double* stat_ptr(int) { return nullptr; }
+  __device__ void finish(int, int) {}
+};
+
+__global__ void k_bn_finalize(const double* __restrict__ sums, int64_t n, int64_t d, float* __restrict__ mean,
+                              float* __restrict__ invstd, GpsBatchNorm bn) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c == 0 && bn.num_batches_tracked) *bn.num_batches_tracked += 1;
+  if (c >= d) return;
+  double m = sums[c] / (double)n;
+  double var = sums[d + c] / (double)n - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[c] = (float)m;
+  invstd[c] = (float)(1.0 / sqrt(var + (double)kBnEps));
+  if (bn.running_mean) bn.running_mean[c] = (1.f - kBnMomentum) * bn.running_mean[c] + kBnMomentum * (float)m;
+  if (bn.running_var) {
+    double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
+    bn.running_var[c] = (1.f - kBnMomentum) * bn.running_var[c] + kBnMomentum * (float)unbiased;
+  }
+}
+
+__global__ void k_bn_eval_prep(int64_t d, float* __restrict__ mean, float* __restrict__ invstd, GpsBatchNorm bn) {
+  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (c >= d) return;
+  mean[c] = bn.running_mean[c];
+  invstd[c] = rsqrtf(bn.running_var[c] + kBnEps);
+}
+
+template <class Op>
+static int launch_rowwise(Op op, int64_t rows, int64_t d, cudaStream_t stream) {
+  if (rows == 0) return GPS_OK;
+  RowGeom g;
+  GPS_TRY(row_geom(rows, d, Op::NS, &g));
+  k_rowwise<Op><<<g.grid, g.block, g.smem, stream>>>(op, rows);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+}  // namespace
+
+int bn_finalize(const double* sums, int64_t n, int64_t d, float* mean, float* invstd, const GpsBatchNorm& bn,
+                cudaStream_t stream) {
+  k_bn_finalize<<<(unsigned)ceil_div(d, 128), 128, 0, stream>>>(sums, n > 0 ? n : 1, d, mean, invstd, bn);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+int bn_eval_prep(int64_t d, float* mean, float* invstd, const GpsBatchNorm& bn, cudaStream_t stream) {
+  GPS_REQUIRE(bn.running_mean && bn.running_var, GPS_ERR_ARG, "eval-mode BatchNorm needs running statistics");
+  k_bn_eval_prep<<<(unsigned)ceil_div(d, 128), 128, 0, stream>>>(d, mean, invstd, bn);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+int bn_act_residual(const float* z, int64_t ldz, const float* R, float* out, int64_t rows, int64_t d, BnView bn,
+                    int act, DropCfg drop, double* stats, cudaStream_t stream) {
+  if (stats) {
+    OpBnActRes<true> op{z, ldz, R, out, d, bn, act, drop, stats};
+    return launch_rowwise(op, rows, d, stream);
+  }
+  OpBnActRes<false> op{z, ldz, R, out, d, bn, act, drop, nullptr};
+  return launch_rowwise(op, rows, d, stream);
+}
+
+int bn_combine(const float* a, BnView bna, const float* b, BnView bnb, float* out, int64_t rows, int64_t d,
+               cudaStream_t stream) {
+  OpCombine op{a, b, out, d, bna, bnb};
+  return launch_rowwise(op, rows, d, stream);
+}
+
+int bn_bwd_reduce(const float* g, int64_t ldg, const float* z, int64_t ldz, int64_t rows, int64_t d, BnView bn,
+                  int act, DropCfg drop, double* sums, cudaStream_t stream) {
+  OpBnBwdReduce op{g, ldg, z, ldz, d, bn, act, drop, sums};
+  return launch_rowwise(op, rows, d, stream);
+}
+
+int bn_bwd_apply(const float* g, int64_t ldg, const float* z, int64_t ldz, int64_t rows, int64_t d, BnView bn,
+                 int act, DropCfg drop, const double* sums, float* out, int64_t ldo, float* grad_gamma,
+                 float* grad_beta, cudaStream_t stream) {
+  OpBnBwdApply op{g, ldg, z, ldz, d, bn, act, drop, sums, 1.f / (float)(rows > 0 ? rows : 1),
+                  out, ldo, grad_gamma, grad_beta};
+  if (rows == 0) {
+    // no rows: gradients of gamma/beta are zero
+    if (grad_gamma) GPS_CUDA(cudaMemsetAsync(grad_gamma, 0, d * sizeof(float), stream));
+    if (grad_beta) GPS_CUDA(cudaMemsetAsync(grad_beta, 0, d * sizeof(float), stream));
+    return GPS_OK;
+  }
+  return launch_rowwise(op, rows, d, stream);
+}
+
+int add3(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, float* out,
+         int64_t ldo, int64_t rows, int64_t d, cudaStream_t stream) {
+  OpAdd3 op{a, lda, b, ldb, c, ldc, out, ldo};
+  return launch_rowwise(op, rows, d, stream);
+}
+
+int copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int64_t d, cudaStream_t stream) {
+  if (rows == 0) return GPS_OK;
+  GPS_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(float), src, lds * sizeof(float), d * sizeof(float), rows,
+                             cudaMemcpyDeviceToDevice, stream));
+  return GPS_OK;
+}
+
+}  // namespace gps

@@ -1,0 +1,40 @@
+// gemm.cuh — parameter block shared by the dense-product kernels (gemm_simt.cu, gemm_tc.cu).
+#pragma once
+#include "common.cuh"
+
+namespace gps {
+
+// C[m,n] (+)= epilogue( sum_k Aop[m,k] * Bop[k,n] )
+//   ta == 0: Aop[m,k] = A[m*lda + k]      ta == 1: Aop[m,k] = A[k*lda + m]
+//   tb == 0: Bop[k,n] = B[n*ldb + k]      tb == 1: Bop[k,n] = B[k*ldb + n]
+// Epilogue order: +bias[n] -> (store pre-activation) -> act -> *act'(mask_src) -> dropout ->
+//                 +R1 +R2 -> store -> column statistics (sum, sum of squares, double atomics).
+// With splitk > 1 the partial products are atomically added into a pre-zeroed C and only the
+// plain product is supported.
+struct GemmParams {
+  int M = 0, N = 0, K = 0;
+  const float* A = nullptr; int lda = 0; int ta = 0;
+  const float* B = nullptr; int ldb = 0; int tb = 0;
+  float* C = nullptr; int ldc = 0;
+  const float* bias = nullptr;
+  float* C_pre = nullptr; int ldpre = 0;   // optional copy of the pre-activation value
+  int act = -1;                            // -1 none, GPS_ACT_*
+  const float* mask_src = nullptr; int ldmask = 0; int mask_act = -1;  // multiply by act'(mask_src)
+  int mask_is_post = 0;                    // relu only: mask_src holds the post-activation value
+  float p_drop = 0.f; uint64_t seed = 0, offset = 0; int site = 0;    // dropout on the result
+  const float* R1 = nullptr; int ldr1 = 0;
+  const float* R2 = nullptr; int ldr2 = 0;
+  double* stats = nullptr;                 // [2][N] column sum / sum of squares of the stored C
+  int splitk = 1;
+  float* colsum_a = nullptr;               // ta==1 only: += sum_k Aop[m,k]  (bias gradient), [M]
+  int precision = GPS_PREC_FP32;
+};
+
+// exact fp32 CUDA-core product (validation path and shapes the tensor-core kernel does not take)
+int gemm_simt(const GemmParams& p, cudaStream_t stream);
+// tcgen05 tensor-core product; returns GPS_ERR_UNSUPPORTED for shapes it does not take
+int gemm_tc(const GemmParams& p, cudaStream_t stream);
+// dispatcher used by the layer
+int gemm(const GemmParams& p, cudaStream_t stream);
+
+}  // namespace gps

@@ -1,0 +1,345 @@
+"""B200-native drop-in for `graphgps.layer.gps_layer.GPSLayer`.
+
+Same constructor signature, `forward(batch) -> batch` contract and `state_dict` layout as the
+reference module (graphgps/layer/gps_layer.py:16-264; parameter names per SURVEY.md section 8b), so
+`graphgps/network/gps_model.py:85-99` can instantiate it unchanged and reference checkpoints load
+with `load_state_dict`.  All arithmetic of the layer — the five GatedGCN projections, the
+CSR/CSC segmented gather-reduce, softmax attention over each graph's node set, residual/BatchNorm/FFN
+and the whole backward pass — runs in hand-written CUDA (libgps_b200.so, sm_100a) reached through
+one C-ABI call per direction; PyTorch only owns memory, streams and the autograd graph edge.
+There is NO fallback: CPU tensors or a missing library raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .graph import graph_of
+
+_SUPPORTED_LOCAL = ("None", "CustomGatedGCN", "GINE")
+_KNOWN_LOCAL = _SUPPORTED_LOCAL + ("GCN", "GIN", "GENConv", "GAT", "PNA")
+_SUPPORTED_GLOBAL = ("None", "Transformer", "Performer")
+_KNOWN_GLOBAL = _SUPPORTED_GLOBAL + ("BiasedTransformer", "BigBird")
+_ACT_MODULES = {"relu": nn.ReLU, "gelu": nn.GELU}
+
+_workspaces = {}
+_dropout_calls = [0]
+
+
+def _workspace(device, nbytes):
+    ws = _workspaces.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+        _workspaces[device] = ws
+    return ws
+
+
+class _GatedGCNParams(nn.Module):
+    """Parameter container with the names of graphgps/layer/gatedgcn_layer.py:21-38."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.A = nn.Linear(dim, dim, bias=True)
+        self.B = nn.Linear(dim, dim, bias=True)
+        self.C = nn.Linear(dim, dim, bias=True)
+        self.D = nn.Linear(dim, dim, bias=True)
+        self.E = nn.Linear(dim, dim, bias=True)
+        self.bn_node_x = nn.BatchNorm1d(dim)
+        self.bn_edge_e = nn.BatchNorm1d(dim)
+
+
+class _GINEParams(nn.Module):
+    """Names of PyG GINEConv(gin_nn) as built at gps_layer.py:62-69: nn.0, nn.2, eps buffer."""
+
+    def __init__(self, dim, act):
+        super().__init__()
+        self.nn = nn.Sequential(nn.Linear(dim, dim), _ACT_MODULES[act](), nn.Linear(dim, dim))
+        self.register_buffer("eps", torch.Tensor([0.0]))
+
+
+def _orthogonal_gaussian_matrix(nb_rows, nb_cols):
+    """Random-feature projection drawn once at construction (performer_layer.py:163-195, scaling=0)."""
+    blocks = []
+    full = nb_rows // nb_cols
+    for _ in range(full):
+        q, _r = torch.linalg.qr(torch.randn(nb_cols, nb_cols), mode="reduced")
+        blocks.append(q.t())
+    rem = nb_rows - full * nb_cols
+    if rem > 0:
+        q, _r = torch.linalg.qr(torch.randn(nb_cols, nb_cols), mode="reduced")
+        blocks.append(q.t()[:rem])
+    final = torch.cat(blocks)
+    mult = torch.randn(nb_rows, nb_cols).norm(dim=1)
+    return torch.diag(mult) @ final
+
+
+class _FastAttentionParams(nn.Module):
+    def __init__(self, dim_head):
+        super().__init__()
+        nb = int(dim_head * math.log(dim_head))  # performer_layer.py:261
+        self.register_buffer("projection_matrix", _orthogonal_gaussian_matrix(nb, dim_head))
+
+
+class _PerformerParams(nn.Module):
+    """Names of performer_pytorch.SelfAttention as built at gps_layer.py:111-114
+    (dim_head=64, qkv_bias=False, attn_out_bias=True; performer_layer.py:421-474)."""
+
+    def __init__(self, dim, heads, dim_head=64):
+        super().__init__()
+        inner = dim_head * heads
+        self.heads, self.dim_head = heads, dim_head
+        self.fast_attention = _FastAttentionParams(dim_head)
+        self.to_q = nn.Linear(dim, inner, bias=False)
+        self.to_k = nn.Linear(dim, inner, bias=False)
+        self.to_v = nn.Linear(dim, inner, bias=False)
+        self.to_out = nn.Linear(inner, dim, bias=True)
+
+
+def _lin(weight, bias, gw=None, gb=None):
+    return _lib.GpsLinear(_lib.ptr(weight), _lib.ptr(bias), _lib.ptr(gw), _lib.ptr(gb))
+
+
+def _bn(mod, gw=None, gb=None):
+    return _lib.GpsBatchNorm(_lib.ptr(mod.weight), _lib.ptr(mod.bias), _lib.ptr(mod.running_mean),
+                             _lib.ptr(mod.running_var), _lib.ptr(mod.num_batches_tracked),
+                             _lib.ptr(gw), _lib.ptr(gb))
+
+
+class _GPSLayerFn(torch.autograd.Function):
+    """One autograd node for the whole layer: forward = gps_layer_forward, backward = gps_layer_backward."""
+
+    @staticmethod
+    def forward(ctx, layer, gs, x, e, *params):
+        lib = _lib.load()
+        dev = x.device
+        named = dict(zip(layer._param_names, params))
+        args = layer._base_args(gs, named)
+        N, E, d = gs.N, gs.E, layer.dim_h
+        x_out = torch.empty_like(x)
+        e_out = torch.empty_like(e) if layer.local_gnn_type == "CustomGatedGCN" else None
+        plan = _lib.GpsLayerPlan()
+        _lib.check(lib.gps_layer_plan(C.byref(args), C.byref(plan)), "gps_layer_plan")
+        saved = torch.empty(max(plan.saved_bytes, 256), dtype=torch.uint8, device=dev)
+        ws = _workspace(dev, max(plan.fwd_workspace_bytes, plan.bwd_workspace_bytes))
+        args.x, args.edge_attr = x.data_ptr(), _lib.ptr(e)
+        args.x_out, args.edge_out = x_out.data_ptr(), _lib.ptr(e_out)
+        args.saved, args.saved_bytes = saved.data_ptr(), saved.numel()
+        args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.gps_layer_forward(C.byref(args), stream), "gps_layer_forward")
+        ctx.layer, ctx.gs, ctx.saved_buf = layer, gs, saved
+        ctx.seed, ctx.offset, ctx.training = args.seed, args.offset, bool(args.training)
+        ctx.save_for_backward(x, e, *params)
+        if e_out is not None:
+            return x_out, e_out
+        return x_out
+
+    @staticmethod
+    def backward(ctx, g_x_out, g_e_out=None):
+        lib = _lib.load()
+        layer, gs = ctx.layer, ctx.gs
+        x, e, *params = ctx.saved_tensors
+        if not ctx.training:
+            raise RuntimeError("GPSLayer backward needs training mode (BatchNorm batch statistics)")
+        dev = x.device
+        named = dict(zip(layer._param_names, params))
+        grads = {n: torch.empty_like(p) for n, p in named.items()}
+        args = layer._base_args(gs, named, grads)
+        args.seed, args.offset, args.training = ctx.seed, ctx.offset, 1
+        g_x_out = g_x_out.contiguous()
+        gated = layer.local_gnn_type == "CustomGatedGCN"
+        if g_e_out is not None:
+            g_e_out = g_e_out.contiguous()
+        g_x = torch.empty_like(x)
+        g_e = torch.empty_like(e) if layer.local_gnn_type != "None" else None
+        plan = _lib.GpsLayerPlan()
+        _lib.check(lib.gps_layer_plan(C.byref(args), C.byref(plan)), "gps_layer_plan")
+        ws = _workspace(dev, max(plan.fwd_workspace_bytes, plan.bwd_workspace_bytes))
+        args.x, args.edge_attr = x.data_ptr(), _lib.ptr(e)
+        args.grad_x_out = g_x_out.data_ptr()
+        args.grad_edge_out = _lib.ptr(g_e_out) if gated else 0
+        args.grad_x, args.grad_edge_attr = g_x.data_ptr(), _lib.ptr(g_e)
+        args.saved, args.saved_bytes = ctx.saved_buf.data_ptr(), ctx.saved_buf.numel()
+        args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.gps_layer_backward(C.byref(args), stream), "gps_layer_backward")
+        ctx.saved_buf = None
+        # parameters the configuration never reads get no gradient (as under autograd in the reference)
+        unused = []
+        if layer.local_gnn_type == "None":
+            unused.append("norm1_local.")
+        if layer.global_model_type == "None":
+            unused.append("norm1_attn.")
+        pg = tuple(None if any(n.startswith(u) for u in unused) else grads[n] for n in layer._param_names)
+        return (None, None, g_x, g_e) + pg
+
+
+class GPSLayer(nn.Module):
+    """Local MPNN + full graph attention x-former layer (reference: gps_layer.py:16-264)."""
+
+    def __init__(self, dim_h, local_gnn_type, global_model_type, num_heads, act="relu",
+                 pna_degrees=None, equivstable_pe=False, dropout=0.0, attn_dropout=0.0,
+                 layer_norm=False, batch_norm=True, bigbird_cfg=None, log_attn_weights=False,
+                 precision="fp32"):
+        super().__init__()
+        self.dim_h = dim_h
+        self.num_heads = num_heads
+        self.attn_dropout = attn_dropout
+        self.dropout = dropout
+        self.layer_norm = layer_norm
+        self.batch_norm = batch_norm
+        self.equivstable_pe = equivstable_pe
+        self.act = act
+        self.precision = precision
+        if act not in _ACT_MODULES:
+            raise NotImplementedError(f"activation '{act}' is not built in graphgps_b200 (relu, gelu)")
+        self.activation = _ACT_MODULES[act]
+        self.log_attn_weights = log_attn_weights
+        if log_attn_weights and global_model_type not in ["Transformer", "BiasedTransformer"]:
+            raise NotImplementedError(                                    # gps_layer.py:36-41
+                f"Logging of attention weights is not supported "
+                f"for '{global_model_type}' global attention model.")
+        if log_attn_weights:
+            raise NotImplementedError("log_attn_weights is not built in graphgps_b200")
+
+        # ---- local message-passing model (gps_layer.py:44-99)
+        self.local_gnn_with_edge_attr = True
+        if local_gnn_type not in _KNOWN_LOCAL:
+            raise ValueError(f"Unsupported local GNN model: {local_gnn_type}")
+        if local_gnn_type not in _SUPPORTED_LOCAL:
+            raise NotImplementedError(f"local GNN '{local_gnn_type}' is not built in graphgps_b200 "
+                                      f"(available: {_SUPPORTED_LOCAL}); there is no fallback path")
+        if equivstable_pe:
+            raise NotImplementedError("equivstable_pe is not built in graphgps_b200")
+        if local_gnn_type == "None":
+            self.local_model = None
+        elif local_gnn_type == "GINE":
+            self.local_model = _GINEParams(dim_h, act)
+        else:
+            self.local_model = _GatedGCNParams(dim_h)
+        self.local_gnn_type = local_gnn_type
+
+        # ---- global attention model (gps_layer.py:101-122)
+        if global_model_type not in _KNOWN_GLOBAL:
+            raise ValueError(f"Unsupported global x-former model: {global_model_type}")
+        if global_model_type not in _SUPPORTED_GLOBAL:
+            raise NotImplementedError(f"global model '{global_model_type}' is not built in graphgps_b200")
+        if global_model_type == "None":
+            self.self_attn = None
+        elif global_model_type == "Transformer":
+            if dim_h % num_heads != 0:
+                raise ValueError("embed_dim must be divisible by num_heads")
+            # torch's own module is the parameter container (same init, same state_dict keys);
+            # its forward is never called.
+            self.self_attn = nn.MultiheadAttention(dim_h, num_heads, dropout=attn_dropout, batch_first=True)
+        else:
+            self.self_attn = _PerformerParams(dim_h, num_heads)
+        self.global_model_type = global_model_type
+
+        if self.layer_norm and self.batch_norm:
+            raise ValueError("Cannot apply two types of normalization together")   # gps_layer.py:125-126
+        if self.layer_norm or not self.batch_norm:
+            raise NotImplementedError("graphgps_b200 builds the BatchNorm configuration "
+                                      "(layer_norm=False, batch_norm=True) used by every shipped config")
+        if self.local_model is None and self.self_attn is None:
+            raise ValueError("GPSLayer needs a local model or a global model")
+        self.norm1_local = nn.BatchNorm1d(dim_h)
+        self.norm1_attn = nn.BatchNorm1d(dim_h)
+        self.ff_linear1 = nn.Linear(dim_h, dim_h * 2)
+        self.ff_linear2 = nn.Linear(dim_h * 2, dim_h)
+        self.norm2 = nn.BatchNorm1d(dim_h)
+        self._param_names = [n for n, _ in self.named_parameters()]
+
+    # ------------------------------------------------------------------------------------
+    def _base_args(self, gs, named, grads=None):
+        """GpsLayerArgs with configuration, graph and parameter (+gradient) pointers filled in."""
+        g = grads or {}
+        a = _lib.GpsLayerArgs()
+        a.d, a.heads = self.dim_h, self.num_heads
+        a.local_type = _lib.LOCAL[self.local_gnn_type]
+        a.global_type = _lib.GLOBAL[self.global_model_type]
+        a.act = _lib.ACT[self.act]
+        a.training = 1 if self.training else 0
+        a.precision = _lib.PRECISION[self.precision]
+        a.dropout, a.attn_dropout = float(self.dropout), float(self.attn_dropout)
+        a.seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        _dropout_calls[0] += 1
+        a.offset = _dropout_calls[0] * 4096
+        a.graph = gs.desc
+
+        def lin(prefix, bias=True):
+            return _lin(named[prefix + ".weight"], named.get(prefix + ".bias") if bias else None,
+                        g.get(prefix + ".weight"), g.get(prefix + ".bias") if bias else None)
+
+        def bn(prefix, mod):
+            return _lib.GpsBatchNorm(_lib.ptr(named[prefix + ".weight"]), _lib.ptr(named[prefix + ".bias"]),
+                                     _lib.ptr(mod.running_mean), _lib.ptr(mod.running_var),
+                                     _lib.ptr(mod.num_batches_tracked),
+                                     _lib.ptr(g.get(prefix + ".weight")), _lib.ptr(g.get(prefix + ".bias")))
+
+        if self.local_gnn_type == "CustomGatedGCN":
+            a.gcn_A, a.gcn_B, a.gcn_C = lin("local_model.A"), lin("local_model.B"), lin("local_model.C")
+            a.gcn_D, a.gcn_E = lin("local_model.D"), lin("local_model.E")
+            a.bn_node_x = bn("local_model.bn_node_x", self.local_model.bn_node_x)
+            a.bn_edge_e = bn("local_model.bn_edge_e", self.local_model.bn_edge_e)
+        elif self.local_gnn_type == "GINE":
+            a.gine_lin0, a.gine_lin1 = lin("local_model.nn.0"), lin("local_model.nn.2")
+            a.gine_eps = float(self._gine_eps_host)
+        if self.global_model_type == "Transformer":
+            a.attn_in = _lin(named["self_attn.in_proj_weight"], named["self_attn.in_proj_bias"],
+                             g.get("self_attn.in_proj_weight"), g.get("self_attn.in_proj_bias"))
+            a.attn_out = lin("self_attn.out_proj")
+        elif self.global_model_type == "Performer":
+            a.perf_q, a.perf_k, a.perf_v = (lin("self_attn.to_q", False), lin("self_attn.to_k", False),
+                                            lin("self_attn.to_v", False))
+            a.attn_out = lin("self_attn.to_out")
+            pm = self.self_attn.fast_attention.projection_matrix
+            a.perf_proj, a.perf_features, a.perf_dim_head = pm.data_ptr(), pm.shape[0], pm.shape[1]
+        a.norm1_local = bn("norm1_local", self.norm1_local)
+        a.norm1_attn = bn("norm1_attn", self.norm1_attn)
+        a.norm2 = bn("norm2", self.norm2)
+        a.ff1, a.ff2 = lin("ff_linear1"), lin("ff_linear2")
+        return a
+
+    @property
+    def _gine_eps_host(self):
+        # eps is a constant buffer (train_eps=False); read once, no per-step sync
+        v = self.__dict__.get("_gine_eps_cache")
+        if v is None:
+            v = float(self.local_model.eps.item())
+            self.__dict__["_gine_eps_cache"] = v
+        return v
+
+    def forward(self, batch):
+        x = batch.x
+        if not x.is_cuda:
+            raise RuntimeError("graphgps_b200.GPSLayer runs on CUDA tensors only; there is no CPU fallback "
+                               "(use the oracle under oracle/ for CPU checks)")
+        if x.dtype != torch.float32:
+            raise TypeError("batch.x must be float32")
+        x = x.contiguous()
+        e = getattr(batch, "edge_attr", None)
+        if self.local_gnn_type != "None":
+            if e is None or e.shape[-1] != self.dim_h:
+                raise ValueError("Node and edge feature dimensionalities do not match")
+            e = e.contiguous()
+        else:
+            e = None
+        gs = graph_of(batch)
+        params = [p for _, p in self.named_parameters()]
+        e_arg = e if e is not None else x.new_empty(0)
+        out = _GPSLayerFn.apply(self, gs, x, e_arg, *params)
+        if self.local_gnn_type == "CustomGatedGCN":
+            batch.x, batch.edge_attr = out           # gps_layer.py:173-174, :231
+        else:
+            batch.x = out
+        return batch
+
+    def extra_repr(self):
+        return (f"summary: dim_h={self.dim_h}, local_gnn_type={self.local_gnn_type}, "
+                f"global_model_type={self.global_model_type}, heads={self.num_heads}, "
+                f"backend=libgps_b200(sm_100a), precision={self.precision}")

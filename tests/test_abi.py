@@ -1,0 +1,70 @@
+"""CPU: the C-ABI library loads and exports every symbol include/gps_b200.h declares; the Python
+module keeps the reference's constructor contract and state_dict layout (no compute calls)."""
+import os
+import re
+
+import pytest
+import torch
+
+import graphgps_b200
+from graphgps_b200 import _lib
+from oracle.gps_oracle import OracleGPSLayer
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "gps_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gps_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = header_symbols()
+    assert len(syms) >= 10
+    for s in syms:
+        assert hasattr(lib, s), f"libgps_b200.so does not export {s}"
+        assert s in _lib.SYMBOLS, f"ctypes binding missing for {s}"
+    assert lib.gps_abi_version() == 1
+    assert lib.gps_build_arch() == b"sm_100a"
+
+
+def test_graph_bytes_is_pure():
+    lib = _lib.load()
+    assert lib.gps_graph_bytes(10, 20, 2) > 0
+    assert lib.gps_graph_bytes(0, 0, 0) >= 0
+
+
+@pytest.mark.parametrize("local,glob", [("CustomGatedGCN", "Transformer"), ("GINE", "Transformer"),
+                                        ("CustomGatedGCN", "Performer"), ("None", "Transformer"),
+                                        ("GINE", "None"), ("CustomGatedGCN", "None")])
+def test_state_dict_layout_matches_reference(local, glob):
+    ours = graphgps_b200.GPSLayer(64, local, glob, 4)
+    ref = OracleGPSLayer(64, local, glob, 4)   # same keys as the reference (tests/test_oracle.py pins that)
+    so, sr = ours.state_dict(), ref.state_dict()
+    assert set(so) == set(sr)
+    for k in so:
+        assert tuple(so[k].shape) == tuple(sr[k].shape), k
+    ours.load_state_dict(sr, strict=True)
+
+
+def test_constructor_errors_follow_reference():
+    G = graphgps_b200.GPSLayer
+    with pytest.raises(ValueError):
+        G(64, "NoSuchGNN", "Transformer", 4)                 # gps_layer.py:98
+    with pytest.raises(ValueError):
+        G(64, "GINE", "NoSuchFormer", 4)                     # gps_layer.py:121
+    with pytest.raises(ValueError):
+        G(64, "GINE", "Transformer", 4, layer_norm=True, batch_norm=True)   # gps_layer.py:125-126
+    with pytest.raises(NotImplementedError):
+        G(64, "GINE", "Performer", 4, log_attn_weights=True)  # gps_layer.py:36-41
+    with pytest.raises(NotImplementedError):
+        G(64, "PNA", "Transformer", 4)                        # known to the reference, not built here
+
+
+def test_cpu_tensors_fail_loudly():
+    layer = graphgps_b200.GPSLayer(32, "CustomGatedGCN", "Transformer", 4)
+    b = graphgps_b200.make_batch("zinc-gatedgcn", dim=32, num_graphs=2)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        layer(b)

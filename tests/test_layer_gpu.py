@@ -1,0 +1,262 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against
+(i) the committed golden fixtures (reference-verbatim, fp64), (ii) the oracle on the same seeded
+inputs, (iii) torch restatements of single stages, and (iv) size-independent properties at the
+BASELINE sizes.  Tolerances: 1e-3 for precision="fp32", 1e-2 for "bf16" (BASELINE.json north_star),
+measured as max|a-b| / max(1, max|b|) on BatchNorm-normalised outputs."""
+import ctypes as C
+
+import pytest
+import torch
+
+import graphgps_b200
+from graphgps_b200 import _lib
+from graphgps_b200.batch import batch_from_lists, make_batch
+from graphgps_b200.graph import GraphStructure, graph_of
+from oracle.gps_oracle import OracleGPSLayer
+from util import compare, golden_batch, golden_names, load_golden, rel_err, run_layer
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+TOL = {"fp32": 1e-3, "bf16": 1e-2}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# ------------------------------------------------------------------------------- graph structure
+@pytest.mark.parametrize("shape,B", [("pcqm4m-small", 64), ("code2", 8), ("zinc-gine", 1)])
+def test_graph_build_matches_sort(shape, B):
+    b = make_batch(shape, seed=1, dim=8, num_graphs=B).to(DEV)
+    gs = GraphStructure(b.edge_index, b.batch, B)
+    torch.cuda.synchronize()
+    src, dst = b.edge_index[0].cpu(), b.edge_index[1].cpu()
+    E, N = src.numel(), b.num_nodes
+    order = torch.argsort(dst * E + torch.arange(E), stable=True)     # by dst, ties by edge id
+    assert torch.equal(gs.dst_eid.cpu().long(), order)
+    assert torch.equal(gs.dst_src.cpu().long(), src[order])
+    assert torch.equal(gs.dst_ptr.cpu().long(), torch.cat([torch.zeros(1, dtype=torch.long),
+                                                           torch.bincount(dst, minlength=N).cumsum(0)]))
+    order_s = torch.argsort(src * E + torch.arange(E), stable=True)
+    assert torch.equal(gs.src_eid.cpu().long(), order_s)
+    assert torch.equal(gs.src_dst.cpu().long(), dst[order_s])
+    assert torch.equal(gs.graph_ptr.cpu().long(), b.ptr)
+
+
+def test_graph_build_empty_graphs_and_no_edges():
+    b = batch_from_lists([3, 0, 2, 0], [[(0, 1), (1, 0), (2, 2)], [], [], []], d=8).to(DEV)
+    gs = GraphStructure(b.edge_index, b.batch, 4)
+    assert gs.graph_ptr.cpu().tolist() == [0, 3, 3, 5, 5]
+    assert gs.dst_ptr.cpu().tolist() == [0, 1, 2, 3, 3, 3]
+
+
+# ------------------------------------------------------------------------------- single stages
+@pytest.mark.parametrize("M,N,K", [(3620, 2128, 304), (7455, 304, 304), (130, 64, 64), (1, 4, 4), (333, 608, 304)])
+def test_linear_forward(M, N, K):
+    lib = _lib.load()
+    g = torch.Generator(device="cpu").manual_seed(0)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    Cc = torch.empty(M, N, device=DEV)
+    rc = lib.gps_linear_forward(A.data_ptr(), K, W.data_ptr(), K, bias.data_ptr(), Cc.data_ptr(), N, M, N, K, -1, 0,
+                                _stream())
+    _lib.check(rc, "gps_linear_forward")
+    ref = (A.double() @ W.double().t() + bias.double()).float()
+    assert rel_err(Cc.cpu(), ref.cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("shape,d", [("pcqm4m-small", 304), ("zinc-gatedgcn", 64), ("code2", 256)])
+def test_gatedgcn_aggregate_forward(shape, d):
+    lib = _lib.load()
+    b = make_batch(shape, seed=2, dim=d, num_graphs=16).to(DEV)
+    gs = graph_of(b)
+    N, E = b.num_nodes, b.num_edges
+    Y = torch.randn(N, 4 * d, device=DEV)
+    Ce = torch.randn(E, d, device=DEV)
+    src, dst = b.edge_index
+    Ax, Bx, Dx, Ex = (Y[:, i * d:(i + 1) * d].double() for i in range(4))
+    e_ij = Dx[dst] + Ex[src] + Ce.double()
+    sig = torch.sigmoid(e_ij)
+    num = torch.zeros(N, d, device=DEV, dtype=torch.float64).index_add_(0, dst, sig * Bx[src])
+    den = torch.zeros(N, d, device=DEV, dtype=torch.float64).index_add_(0, dst, sig)
+    xt_ref = Ax + num / (den + 1e-6)
+    xt = torch.empty(N, d, device=DEV)
+    sx = torch.zeros(2, d, device=DEV, dtype=torch.float64)
+    se = torch.zeros(2, d, device=DEV, dtype=torch.float64)
+    rc = lib.gps_gatedgcn_aggregate_forward(C.byref(gs.desc), d, Y.data_ptr(), Y.data_ptr() + 4 * d,
+                                            Y.data_ptr() + 8 * d, Y.data_ptr() + 12 * d, 4 * d, Ce.data_ptr(),
+                                            xt.data_ptr(), sx.data_ptr(), se.data_ptr(), _stream())
+    _lib.check(rc, "gatedgcn_aggregate")
+    assert rel_err(xt.cpu(), xt_ref.cpu()) < 2e-5
+    assert rel_err(Ce.cpu(), e_ij.cpu()) < 1e-5
+    assert rel_err(sx[0].cpu(), xt_ref.sum(0).cpu()) < 1e-4 and rel_err(sx[1].cpu(), (xt_ref ** 2).sum(0).cpu()) < 1e-4
+    assert rel_err(se[0].cpu(), e_ij.sum(0).cpu()) < 1e-4 and rel_err(se[1].cpu(), (e_ij ** 2).sum(0).cpu()) < 1e-4
+
+
+def _dense_attention_ref(Q, K, V, ptr, H):
+    outs = []
+    N, D = Q.shape
+    hd = D // H
+    for g in range(len(ptr) - 1):
+        s, e = int(ptr[g]), int(ptr[g + 1])
+        if e == s:
+            continue
+        q = Q[s:e].view(e - s, H, hd).transpose(0, 1)
+        k = K[s:e].view(e - s, H, hd).transpose(0, 1)
+        v = V[s:e].view(e - s, H, hd).transpose(0, 1)
+        p = torch.softmax(q @ k.transpose(1, 2) / hd ** 0.5, dim=-1)
+        outs.append((p @ v).transpose(0, 1).reshape(e - s, D))
+    return torch.cat(outs)
+
+
+@pytest.mark.parametrize("shape,H,hd,B", [("pcqm4m-small", 4, 76, 32), ("zinc-gatedgcn", 4, 16, 8),
+                                          ("pcqm4m-small", 16, 24, 16), ("code2", 4, 64, 6)])
+def test_attention_forward_backward(shape, H, hd, B):
+    lib = _lib.load()
+    D = H * hd
+    b = make_batch(shape, seed=4, dim=8, num_graphs=B).to(DEV)
+    gs = graph_of(b)
+    N = b.num_nodes
+    QKV = torch.randn(N, 3 * D, device=DEV)
+    O = torch.empty(N, D, device=DEV)
+    lse = torch.empty(N, H, device=DEV)
+    base = QKV.data_ptr()
+    rc = lib.gps_attention_forward(C.byref(gs.desc), H, hd, base, base + 4 * D, base + 8 * D, 3 * D, O.data_ptr(), D,
+                                   lse.data_ptr(), 0.0, 0, 0, _stream())
+    _lib.check(rc, "attention_forward")
+    q = QKV[:, :D].double().requires_grad_(True)
+    k = QKV[:, D:2 * D].double().requires_grad_(True)
+    v = QKV[:, 2 * D:].double().requires_grad_(True)
+    ref = _dense_attention_ref(q, k, v, b.ptr, H)
+    assert rel_err(O.cpu(), ref.detach().cpu()) < 2e-5
+    dO = torch.randn(N, D, device=DEV)
+    ref.backward(dO.double())
+    dQKV = torch.empty(N, 3 * D, device=DEV)
+    delta = torch.empty(N, H, device=DEV)
+    gb = dQKV.data_ptr()
+    rc = lib.gps_attention_backward(C.byref(gs.desc), H, hd, base, base + 4 * D, base + 8 * D, 3 * D, O.data_ptr(),
+                                    dO.data_ptr(), D, lse.data_ptr(), delta.data_ptr(), gb, gb + 4 * D, gb + 8 * D,
+                                    3 * D, 0.0, 0, 0, _stream())
+    _lib.check(rc, "attention_backward")
+    assert rel_err(dQKV[:, :D].cpu(), q.grad.cpu()) < 5e-5
+    assert rel_err(dQKV[:, D:2 * D].cpu(), k.grad.cpu()) < 5e-5
+    assert rel_err(dQKV[:, 2 * D:].cpu(), v.grad.cpu()) < 5e-5
+
+
+# ------------------------------------------------------------------------------- whole layer
+def _build(cfg, precision="fp32", **kw):
+    layer = graphgps_b200.GPSLayer(cfg["d"], cfg["local"], cfg["glob"], cfg["heads"], act=cfg["act"],
+                                   precision=precision, **kw)
+    return layer
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", golden_names())
+def test_layer_matches_golden(name, precision):
+    fix = load_golden(name)
+    cfg = fix["config"]
+    if cfg["glob"] == "Performer":
+        pytest.xfail("Performer global model not built yet")
+    layer = _build(cfg, precision)
+    layer.load_state_dict(fix["state"], strict=True)
+    layer = layer.to(DEV).train(cfg["training"])
+    res = run_layer(layer, golden_batch(fix, DEV), fix, backward=cfg["training"])
+    errs = compare(res, fix, TOL[precision], f"CUDA {precision} vs golden {name}")
+    print(name, precision, "max err", max(errs.values()))
+
+
+@pytest.mark.parametrize("shape,local,glob,heads", [("pcqm4m-small", "CustomGatedGCN", "Transformer", 4),
+                                                    ("zinc-gine", "GINE", "Transformer", 4),
+                                                    ("code2", "CustomGatedGCN", "Transformer", 4)])
+def test_layer_matches_oracle_full_size(shape, local, glob, heads):
+    """BASELINE-size batch: CUDA layer vs the fp32 oracle on the same seeded inputs and weights."""
+    spec = graphgps_b200.SHAPES[shape]
+    torch.manual_seed(0)
+    ora = OracleGPSLayer(spec.dim, local, glob, heads)
+    ours = graphgps_b200.GPSLayer(spec.dim, local, glob, heads)
+    ours.load_state_dict(ora.state_dict())
+    ours = ours.to(DEV)
+    b = make_batch(shape, seed=7)
+    g = torch.Generator().manual_seed(9)
+    fix = {"config": dict(local=local), "ct_x": torch.randn(b.x.shape, generator=g),
+           "ct_e": torch.randn(b.edge_attr.shape, generator=g)}
+    ref = run_layer(ora.double(), _to(b.clone(), "cpu", torch.float64), fix)
+    res = run_layer(ours, b.clone().to(DEV), fix)
+    tgt = {k: ref[k] for k in ("out_x", "out_e", "grad_x", "grad_e") if k in ref}
+    tgt["grad_params"], tgt["state_after"] = ref["grad_params"], ref["state_after"]
+    compare(res, tgt, 1e-3, f"CUDA fp32 vs oracle fp64 @ {shape}")
+
+
+def _to(b, dev, dt):
+    b.x, b.edge_attr = b.x.to(dev, dt), b.edge_attr.to(dev, dt)
+    return b
+
+
+def test_edge_order_invariance_full_size():
+    """Property: permuting the edge list permutes edge outputs and leaves node outputs unchanged."""
+    torch.manual_seed(1)
+    layer = graphgps_b200.GPSLayer(304, "CustomGatedGCN", "Transformer", 4).to(DEV).eval()
+    b = make_batch("pcqm4m-small", seed=3).to(DEV)
+    perm = torch.randperm(b.num_edges, device=DEV)
+    b2 = graphgps_b200.GraphBatch(x=b.x.clone(), edge_index=b.edge_index[:, perm].contiguous(),
+                                  edge_attr=b.edge_attr[perm].contiguous(), batch=b.batch, num_graphs=b.num_graphs)
+    with torch.no_grad():
+        o1 = layer(b.clone())
+        o2 = layer(b2)
+    assert rel_err(o2.x.cpu(), o1.x.cpu()) < 1e-5
+    assert rel_err(o2.edge_attr.cpu(), o1.edge_attr[perm].cpu()) < 1e-5
+
+
+def test_graphs_are_independent_in_eval_mode():
+    """Property: with running statistics (eval) a graph's output does not depend on its batch mates —
+    i.e. the per-graph mask of the attention is applied (no leakage across graphs), at BASELINE size."""
+    torch.manual_seed(2)
+    layer = graphgps_b200.GPSLayer(304, "CustomGatedGCN", "Transformer", 4).to(DEV).eval()
+    big = make_batch("pcqm4m-small", seed=5)
+    n0, n1 = int(big.ptr[10]), int(big.ptr[11])
+    emask = (big.edge_index[0] >= n0) & (big.edge_index[0] < n1)
+    single = graphgps_b200.GraphBatch(x=big.x[n0:n1].clone(), edge_index=big.edge_index[:, emask] - n0,
+                                      edge_attr=big.edge_attr[emask].clone(),
+                                      batch=torch.zeros(n1 - n0, dtype=torch.int64), num_graphs=1)
+    with torch.no_grad():
+        ob = layer(big.clone().to(DEV))
+        os_ = layer(single.to(DEV))
+    assert rel_err(os_.x.cpu(), ob.x[n0:n1].cpu()) < 1e-4
+    assert rel_err(os_.edge_attr.cpu(), ob.edge_attr[emask.to(DEV)].cpu()) < 1e-4
+
+
+def test_empty_graphs_isolated_nodes_and_no_edges():
+    torch.manual_seed(3)
+    d = 32
+    b = batch_from_lists([4, 0, 1, 3], [[(0, 1), (1, 0), (2, 1)], [], [], []], d=d)
+    ora = OracleGPSLayer(d, "CustomGatedGCN", "Transformer", 4)
+    ours = graphgps_b200.GPSLayer(d, "CustomGatedGCN", "Transformer", 4)
+    ours.load_state_dict(ora.state_dict())
+    ours = ours.to(DEV)
+    g = torch.Generator().manual_seed(1)
+    fix = {"config": dict(local="CustomGatedGCN"), "ct_x": torch.randn(b.x.shape, generator=g),
+           "ct_e": torch.randn(b.edge_attr.shape, generator=g)}
+    ref = run_layer(ora.double(), _to(b.clone(), "cpu", torch.float64), fix)
+    res = run_layer(ours, b.clone().to(DEV), fix)
+    tgt = {k: ref[k] for k in ("out_x", "out_e", "grad_x", "grad_e")}
+    tgt["grad_params"], tgt["state_after"] = ref["grad_params"], ref["state_after"]
+    compare(res, tgt, 1e-3, "edge cases")
+
+
+def test_running_stats_and_eval_after_train():
+    fix = load_golden("gatedgcn_transformer_relu")
+    cfg = fix["config"]
+    ours = _build(cfg).to(DEV)
+    ours.load_state_dict(fix["state"])
+    ora = OracleGPSLayer(cfg["d"], cfg["local"], cfg["glob"], cfg["heads"])
+    ora.load_state_dict(fix["state"])
+    for _ in range(2):
+        ours(golden_batch(fix, DEV))
+        ora(golden_batch(fix))
+    ours.eval(), ora.eval()
+    with torch.no_grad():
+        a = ours(golden_batch(fix, DEV))
+        r = ora(golden_batch(fix))
+    assert rel_err(a.x.cpu(), r.x) < 1e-3 and rel_err(a.edge_attr.cpu(), r.edge_attr) < 1e-3
+    assert int(ours.norm2.num_batches_tracked) == int(ora.norm2.num_batches_tracked) == 2

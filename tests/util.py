@@ -1,0 +1,73 @@
+"""Shared helpers for the parity tests."""
+import glob
+import os
+
+import torch
+
+from graphgps_b200.batch import GraphBatch
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_names():
+    return sorted(os.path.basename(p)[:-3] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.pt")))
+
+
+def load_golden(name):
+    return torch.load(os.path.join(GOLDEN_DIR, name + ".pt"), weights_only=False)
+
+
+def golden_batch(fix, device="cpu", dtype=torch.float32):
+    return GraphBatch(x=fix["x"].to(device=device, dtype=dtype), edge_index=fix["edge_index"].to(device),
+                      edge_attr=fix["edge_attr"].to(device=device, dtype=dtype), batch=fix["batch"].to(device),
+                      num_graphs=fix["num_graphs"])
+
+
+def run_layer(layer, batch, fix, backward=True):
+    """forward (+backward with the fixture's cotangents). Returns dict of outputs/grads on CPU."""
+    cfg = fix["config"]
+    batch.x.requires_grad_(backward)
+    batch.edge_attr.requires_grad_(backward)
+    x_in, e_in = batch.x, batch.edge_attr
+    out = layer(batch)
+    res = {"out_x": out.x.detach().cpu()}
+    dev, dt = out.x.device, out.x.dtype
+    loss = (out.x * fix["ct_x"].to(device=dev, dtype=dt)).sum()
+    if cfg["local"] == "CustomGatedGCN":
+        res["out_e"] = out.edge_attr.detach().cpu()
+        loss = loss + (out.edge_attr * fix["ct_e"].to(device=dev, dtype=dt)).sum()
+    if backward:
+        loss.backward()
+        res["grad_x"] = x_in.grad.detach().cpu()
+        if e_in.grad is not None:
+            res["grad_e"] = e_in.grad.detach().cpu()
+        res["grad_params"] = {n: p.grad.detach().cpu() for n, p in layer.named_parameters() if p.grad is not None}
+    res["state_after"] = {k: v.detach().cpu() for k, v in layer.state_dict().items()
+                          if "running" in k or "num_batches" in k}
+    return res
+
+
+def rel_err(a, b):
+    """max |a-b| / max(1, max|b|): absolute on O(1) (BatchNorm-normalised) data, relative on large."""
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / max(1.0, float(b.abs().max())))
+
+
+def compare(res, fix, tol, what=""):
+    errs = {}
+    for k in ("out_x", "out_e", "grad_x", "grad_e"):
+        if k in fix and k in res:
+            errs[k] = rel_err(res[k], fix[k])
+    for n, g in fix.get("grad_params", {}).items():
+        if n in res.get("grad_params", {}):
+            errs["grad:" + n] = rel_err(res["grad_params"][n], g)
+        else:
+            errs["grad:" + n] = float("inf")
+    for n, v in fix.get("state_after", {}).items():
+        if v.is_floating_point():
+            errs["state:" + n] = rel_err(res["state_after"][n], v)
+        else:
+            errs["state:" + n] = float((res["state_after"][n] != v).any())
+    bad = {k: v for k, v in errs.items() if not v <= tol}
+    assert not bad, f"{what} tolerance {tol} exceeded: {bad}"
+    return errs
