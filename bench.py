@@ -1,0 +1,411 @@
+"""bench.py — graphs/sec through GPSLayer forward+backward on PCQM4M-shaped synthetic batches.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one GPSLayer forward+backward (training mode, BatchNorm batch statistics, dropout as
+configured by configs/GPS/pcqm4m-GPS+RWSE.yaml: dropout 0.0, attn_dropout 0.5) over one synthetic
+256-graph PCQM4Mv2-shaped mini-batch per GPU.  For N > 1 every rank
+processes its own mini-batch (weak scaling) and the parameter gradients are all-reduced over NCCL
+inside the step.  One JSON line is printed by rank 0.
+
+  value     graphs/s with inputs resident in HBM, CUDA-event timed per step, L2 flushed between steps
+  e2e       same metric through the public API with HOST (pinned) inputs: H2D of x/edge_attr/
+            edge_index/batch, graph build, fwd+bwd, D2H of x_out and grad_x inside the timed region
+  roofline  dominant kernel of the step, timed live with CUDA events around its C-ABI stage call
+  cpu_baseline  the reference's own GPSLayer (oracle/_ref run verbatim under oracle/ref_shim.py; the
+            oracle port if the files are absent) on the host cores, bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (shape key, local, global, heads, dropout, attn_dropout, config file it mirrors)
+    "pcqm4m-small": ("pcqm4m-small", "CustomGatedGCN", "Transformer", 4, 0.0, 0.5, "configs/GPS/pcqm4m-GPS+RWSE.yaml"),
+    "zinc-gatedgcn": ("zinc-gatedgcn", "CustomGatedGCN", "Transformer", 4, 0.0, 0.5, "configs/GPS/zinc-GPS+RWSE.yaml"),
+    "zinc-gine": ("zinc-gine", "GINE", "Transformer", 4, 0.0, 0.5, "configs/GPS/zinc-GPS+RWSE.yaml"),
+    "code2": ("code2", "CustomGatedGCN", "Transformer", 4, 0.2, 0.2, "configs/GPS/ogbg-code2-GPS.yaml"),
+}
+NUM_BATCHES = 8          # rotating distinct batches
+L2_FLUSH_BYTES = 256 << 20
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor=p["bf16_tflops"], tensor_sustained=p["bf16_tflops_sustained"],
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tensor=1590.0, tensor_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clock/throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [t.strip() for t in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(name, seed, device=None):
+    import graphgps_b200
+    shape, local, glob, heads, drop, adrop, _ = WORKLOADS[name]
+    spec = graphgps_b200.SHAPES[shape]
+    batches = [graphgps_b200.make_batch(shape, seed=seed * 1000 + i) for i in range(NUM_BATCHES)]
+    return spec, local, glob, heads, drop, adrop, batches
+
+
+# ================================================================================ reference arm
+def cpu_reference_layer(spec, local, glob, heads, drop, adrop):
+    """The reference's own GPSLayer on the CPU (oracle/_ref verbatim under the shim) or the port."""
+    from oracle.ref_shim import find_reference_layer_dir, load_reference
+    torch.manual_seed(0)
+    if find_reference_layer_dir() is not None:
+        ref = load_reference()
+        return ref.GPSLayer(spec.dim, local, glob, heads, dropout=drop, attn_dropout=adrop), "reference"
+    from oracle.gps_oracle import OracleGPSLayer
+    return OracleGPSLayer(spec.dim, local, glob, heads, dropout=drop, attn_dropout=adrop), "port"
+
+
+def time_cpu(layer, batches, steps, warmup, local):
+    layer.train()
+    times = []
+    for it in range(warmup + steps):
+        b = batches[it % len(batches)].clone()
+        b.x.requires_grad_(True)
+        b.edge_attr.requires_grad_(True)
+        for p in layer.parameters():
+            p.grad = None
+        t0 = time.perf_counter()
+        out = layer(b)
+        loss = out.x.sum() + (out.edge_attr.sum() if local == "CustomGatedGCN" else 0.0)
+        loss.backward()
+        t1 = time.perf_counter()
+        if it >= warmup:
+            times.append(t1 - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    spec, local, glob, heads, drop, adrop, batches = make_workload(args.workload, seed=0)
+    layer, kind = cpu_reference_layer(spec, local, glob, heads, drop, adrop)
+    steps = min(args.steps, 20)   # bounded sample: ~0.25 s per step at C3
+    times = time_cpu(layer, batches, steps, min(args.warmup, 3), local)
+    total = sum(times)
+    B = spec.num_graphs
+    value = B * len(times) / total
+    out = {
+        "impl": "reference", "metric": "graphs/sec GPSLayer fwd+bwd", "value": value, "unit": "graphs/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 3),
+        "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, spec, local, glob, heads, drop, adrop, 1),
+        "cpu_baseline": {"value": value, "unit": "graphs/s", "cores": cores, "kind": kind,
+                         "sample": f"{len(times)} steps of one {B}-graph batch fwd+bwd, torch fp32, {cores} threads"},
+        "e2e": {"value": value, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(name, spec, local, glob, heads, drop, adrop, n_gpus):
+    return {"workload": f"{name}: one GPSLayer({local}+{glob}) fwd+bwd, d={spec.dim} H={heads}, "
+                        f"{spec.num_graphs} graphs/GPU (~{spec.n_mean:.0f} nodes/graph), dropout={drop} "
+                        f"attn_dropout={adrop}; mirrors {WORKLOADS[name][6]}",
+            "graphs_per_gpu": spec.num_graphs, "global_batch": spec.num_graphs * n_gpus,
+            "parallelism": f"dp{n_gpus}", "l2": f"flushed between steps ({L2_FLUSH_BYTES >> 20} MiB write) and "
+                                                f"{NUM_BATCHES} rotating batches"}
+
+
+# ================================================================================ our arm
+def run_ours(args):
+    import graphgps_b200
+    from graphgps_b200 import _lib
+    from graphgps_b200.graph import graph_of
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a GPU: graphgps_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    spec, local, glob, heads, drop, adrop, cpu_batches = make_workload(args.workload, seed=rank)
+    torch.manual_seed(0)
+    layer = graphgps_b200.GPSLayer(spec.dim, local, glob, heads, dropout=drop, attn_dropout=adrop,
+                                   precision=args.precision).to(dev).train()
+    params = [p for p in layer.parameters()]
+    gated = local == "CustomGatedGCN"
+
+    dev_batches = [b.clone().to(dev) for b in cpu_batches]
+    for b in dev_batches:
+        graph_of(b)                     # structure is per-batch, amortised over the L layers of a model
+    gen = torch.Generator().manual_seed(1)
+    cts = [(torch.randn(b.x.shape, generator=gen).to(dev), torch.randn(b.edge_attr.shape, generator=gen).to(dev))
+           for b in cpu_batches]
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    grad_bucket = None
+
+    def allreduce_grads():
+        nonlocal grad_bucket
+        if world == 1:
+            return
+        from graphgps_b200.dp import allreduce_gradients
+        grad_bucket = allreduce_gradients(params, grad_bucket)
+
+    def step(i, bobj=None):
+        b = bobj if bobj is not None else dev_batches[i % NUM_BATCHES]
+        ctx, cte = cts[i % NUM_BATCHES]
+        bb = graphgps_b200.GraphBatch(x=b.x.detach().requires_grad_(True), edge_index=b.edge_index,
+                                      edge_attr=b.edge_attr.detach().requires_grad_(True), batch=b.batch,
+                                      num_graphs=b.num_graphs)
+        if "_gps_b200_graph" in b.__dict__:
+            bb.__dict__["_gps_b200_graph"] = b.__dict__["_gps_b200_graph"]
+        for p in params:
+            p.grad = None
+        x_in = bb.x
+        out = layer(bb)
+        if gated:
+            torch.autograd.backward([out.x, out.edge_attr], [ctx, cte])
+        else:
+            torch.autograd.backward([out.x], [ctx])
+        allreduce_grads()
+        return out, x_in
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    evs = []
+    l0 = lib.gps_launch_count()
+    for i in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step(i)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = (lib.gps_launch_count() - l0) // max(1, args.steps)
+    ms = sum(a.elapsed_time(b) for a, b in evs)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+
+    # ---------------- end-to-end through the public API with host buffers
+    pinned = [b.clone().pin_memory() for b in cpu_batches]
+    host_out = torch.empty(cpu_batches[0].x.shape[0] + 64, spec.dim).pin_memory()
+    h2d = d2h = 0
+
+    def e2e_step(i):
+        nonlocal h2d, d2h
+        hb = pinned[i % NUM_BATCHES]
+        b = graphgps_b200.GraphBatch(x=hb.x.to(dev, non_blocking=True), edge_index=hb.edge_index.to(dev, non_blocking=True),
+                                     edge_attr=hb.edge_attr.to(dev, non_blocking=True),
+                                     batch=hb.batch.to(dev, non_blocking=True), num_graphs=hb.num_graphs)
+        h2d = sum(t.numel() * t.element_size() for t in (hb.x, hb.edge_index, hb.edge_attr, hb.batch))
+        out, x_in = step(i, b)
+        n = out.x.shape[0]
+        ho = host_out[:n] if n <= host_out.shape[0] else torch.empty(n, spec.dim).pin_memory()
+        ho.copy_(out.x.detach(), non_blocking=True)
+        ho.copy_(x_in.grad, non_blocking=True)
+        d2h = 2 * n * spec.dim * 4
+
+    for i in range(min(3, args.warmup)):
+        e2e_step(i)
+    barrier()
+    e_evs = []
+    for i in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_step(i)
+        e1.record()
+        e_evs.append((e0, e1))
+    barrier()
+    e_ms = sum(a.elapsed_time(b) for a, b in e_evs)
+    t = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e_ms_total = float(t.item())
+
+    if rank == 0:
+        B = spec.num_graphs
+        value = B * world * args.steps / (ms_total * 1e-3)
+        e2e_value = B * world * args.steps / (e_ms_total * 1e-3)
+        roof = roofline_probe(lib, layer, dev_batches[0], spec, heads, args)
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        ref_layer, kind = cpu_reference_layer(spec, local, glob, heads, drop, adrop)
+        ct = time_cpu(ref_layer, cpu_batches, 8, 2, local)
+        cpu_value = B * len(ct) / sum(ct)
+        out = {
+            "metric": "graphs/sec GPSLayer fwd+bwd", "value": value, "unit": "graphs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
+            "config": workload_config(args.workload, spec, local, glob, heads, drop, adrop, world),
+            "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e_ms_total / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "cpu_baseline": {"value": cpu_value, "unit": "graphs/s", "cores": cores, "kind": kind,
+                             "sample": f"{len(ct)} steps of one {B}-graph batch fwd+bwd (same workload), "
+                                       f"torch fp32, {cores} threads"},
+            "stack": {"layers": spec.layers, "graphs_per_s": value / spec.layers},
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def roofline_probe(lib, layer, b, spec, heads, args):
+    """Times the step's dominant kernel live: the node-projection GEMM (tensor bound) and the GatedGCN
+    segmented gather-reduce (HBM bound) through their C-ABI stage calls; reports the slower one."""
+    import ctypes as C
+    from graphgps_b200.graph import graph_of
+    pk = peaks()
+    gs = graph_of(b)
+    dev = b.x.device
+    N, E, d = gs.N, gs.E, spec.dim
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    res = {}
+
+    def timeit(fn, reps=10):
+        for _ in range(3):
+            fn()
+        tot = 0.0
+        for _ in range(reps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            tot += e0.elapsed_time(e1)
+        return tot / reps * 1e-3
+
+    # (1) node projections [N, 7d] = x [N,d] . Wcat^T : 2*N*7d*d flop
+    Wy = 7 * d
+    W = torch.randn(Wy, d, device=dev) / d ** 0.5
+    bias = torch.zeros(Wy, device=dev)
+    Y = torch.empty(N, Wy, device=dev)
+    prec = 0 if args.precision == "fp32" else 1
+    t_g = timeit(lambda: lib.gps_linear_forward(b.x.data_ptr(), d, W.data_ptr(), d, bias.data_ptr(), Y.data_ptr(), Wy,
+                                                N, Wy, d, -1, prec, stream))
+    flops = 2.0 * N * Wy * d
+    res["gemm"] = {"bound": "tensor", "achieved": flops / t_g / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
+                   "frac": flops / t_g / 1e12 / pk["tensor"], "traffic": None, "seconds": t_g,
+                   "kernel": "node projection GEMM [N,7d]=[N,d]x[7d,d]^T", "peak_source": pk["source"]}
+    # (2) GatedGCN gather-reduce: algorithmic bytes s*(5N+2E)*d
+    Ce = torch.randn(E, d, device=dev)
+    xt = torch.empty(N, d, device=dev)
+    sx = torch.zeros(2, d, device=dev, dtype=torch.float64)
+    se = torch.zeros(2, d, device=dev, dtype=torch.float64)
+    t_s = timeit(lambda: lib.gps_gatedgcn_aggregate_forward(C.byref(gs.desc), d, Y.data_ptr(), Y.data_ptr() + 4 * d,
+                                                            Y.data_ptr() + 8 * d, Y.data_ptr() + 12 * d, Wy,
+                                                            Ce.data_ptr(), xt.data_ptr(), sx.data_ptr(), se.data_ptr(),
+                                                            stream))
+    nbytes = 4.0 * (5 * N + 2 * E) * d
+    res["scatter"] = {"bound": "hbm", "achieved": nbytes / t_s / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                      "frac": nbytes / t_s / 1e9 / pk["hbm"], "traffic": None, "seconds": t_s,
+                      "kernel": "GatedGCN CSR segmented gather-reduce (fwd)", "peak_source": pk["source"]}
+    dom = "gemm" if t_g >= t_s else "scatter"
+    out = dict(res[dom])
+    out["other"] = res["scatter" if dom == "gemm" else "gemm"]
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pcqm4m-small", choices=sorted(WORKLOADS))
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

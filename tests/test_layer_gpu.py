@@ -40,7 +40,7 @@ def test_graph_build_matches_sort(shape, B):
     order_s = torch.argsort(src * E + torch.arange(E), stable=True)
     assert torch.equal(gs.src_eid.cpu().long(), order_s)
     assert torch.equal(gs.src_dst.cpu().long(), dst[order_s])
-    assert torch.equal(gs.graph_ptr.cpu().long(), b.ptr)
+    assert torch.equal(gs.graph_ptr.cpu().long(), b.ptr.cpu())
 
 
 def test_graph_build_empty_graphs_and_no_edges():
@@ -170,7 +170,13 @@ def test_layer_matches_golden(name, precision):
                                                     ("zinc-gine", "GINE", "Transformer", 4),
                                                     ("code2", "CustomGatedGCN", "Transformer", 4)])
 def test_layer_matches_oracle_full_size(shape, local, glob, heads):
-    """BASELINE-size batch: CUDA layer vs the fp32 oracle on the same seeded inputs and weights."""
+    """BASELINE-size batch: CUDA layer vs the oracle on the same seeded inputs and weights.
+
+    Forward outputs: 1e-3 against the fp64 oracle.  Gradients: 1e-3 against the fp32 oracle (the
+    arithmetic the reference itself runs in) and, against fp64, 1e-3 or twice the fp32 oracle's own
+    deviation from fp64, whichever is larger — at ~2M hidden units a single ReLU-kink flip between
+    fp32 and fp64 moves one weight-gradient entry by more than 1e-3 in the reference too."""
+    import copy
     spec = graphgps_b200.SHAPES[shape]
     torch.manual_seed(0)
     ora = OracleGPSLayer(spec.dim, local, glob, heads)
@@ -181,11 +187,23 @@ def test_layer_matches_oracle_full_size(shape, local, glob, heads):
     g = torch.Generator().manual_seed(9)
     fix = {"config": dict(local=local), "ct_x": torch.randn(b.x.shape, generator=g),
            "ct_e": torch.randn(b.edge_attr.shape, generator=g)}
-    ref = run_layer(ora.double(), _to(b.clone(), "cpu", torch.float64), fix)
+    ref64 = run_layer(copy.deepcopy(ora).double(), _to(b.clone(), "cpu", torch.float64), fix)
+    ref32 = run_layer(ora, b.clone(), fix)
     res = run_layer(ours, b.clone().to(DEV), fix)
-    tgt = {k: ref[k] for k in ("out_x", "out_e", "grad_x", "grad_e") if k in ref}
-    tgt["grad_params"], tgt["state_after"] = ref["grad_params"], ref["state_after"]
-    compare(res, tgt, 1e-3, f"CUDA fp32 vs oracle fp64 @ {shape}")
+
+    def target(ref):
+        t = {k: ref[k] for k in ("out_x", "out_e", "grad_x", "grad_e") if k in ref}
+        t["grad_params"], t["state_after"] = ref["grad_params"], ref["state_after"]
+        return t
+    compare(res, target(ref32), 1e-3, f"CUDA fp32 vs oracle fp32 @ {shape}")
+    for k in ("out_x", "out_e"):
+        if k in ref64:
+            assert rel_err(res[k], ref64[k]) < 1e-3, k
+    for k in ("grad_x", "grad_e"):
+        if k in ref64:
+            assert rel_err(res[k], ref64[k]) < max(1e-3, 2 * rel_err(ref32[k], ref64[k])), k
+    for n, gp in ref64["grad_params"].items():
+        assert rel_err(res["grad_params"][n], gp) < max(1e-3, 2 * rel_err(ref32["grad_params"][n], gp)), n
 
 
 def _to(b, dev, dt):
