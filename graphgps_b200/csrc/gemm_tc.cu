@@ -1,7 +1,522 @@
-// gemm_tc.cu — tcgen05 tensor-core dense product (placeholder until the sm_100a kernel lands;
-// returns GPS_ERR_UNSUPPORTED so the dispatcher uses the exact CUDA-core kernel).
+// gemm_tc.cu — tcgen05 (5th-gen tensor core) dense product for every Linear of the GPS layer and
+// their data/weight gradients, with the layer's fused epilogues.
+//
+//   C[M,N] (+)= epi( Aop[M,K] * Bop[K,N] ),  fp32 in HBM, bf16 operands on the tensor cores,
+//   fp32 accumulation in TMEM.  precision FP32: split-bf16 x3 (hi*hi + hi*lo + lo*hi, ~2^-16
+//   relative), precision BF16: a single bf16 pass.
+//
+// Structure (one 128 x BN output tile per CTA, BN a runtime multiple of 16 up to 256):
+//   * warps 0-7 (256 threads) stage operands: coalesced 128-bit global loads of the fp32 tiles ->
+//     bf16 hi/lo split in registers -> 16-byte st.shared into the canonical UMMA SWIZZLE_128B
+//     layout (K-major when the reduction dim is contiguous in HBM, MN-major when it is the row
+//     dim, e.g. weight gradients dW = G^T X) -> fence.proxy.async -> mbarrier arrive.
+//     No transposes, no separate conversion pass, and the fp32->bf16 split costs no extra HBM bytes.
+//   * warp 8: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16) per
+//     16-wide K step, tcgen05.commit releases the smem stage / signals the epilogue.
+//   * epilogue (warps 0-7): tcgen05.ld 32x32b.x16 -> bias / activation / act' mask / dropout /
+//     residuals / 128-bit stores; BatchNorm column sums by a warp butterfly reduce-scatter + double
+//     atomics; split-K partials by fp32 atomics.
+// Smem stages form an mbarrier ring (full: 256 producer arrivals; empty: tcgen05.commit).
+#include <cuda_bf16.h>
+
 #include "gemm.cuh"
 
 namespace gps {
-int gemm_tc(const GemmParams&, cudaStream_t) { return GPS_ERR_UNSUPPORTED; }
+
+namespace {
+
+constexpr int BM = 128;          // UMMA M
+constexpr int BK = 64;           // k-block: one 128-byte swizzle row of bf16
+constexpr int kProducerThreads = 256;
+constexpr int kThreads = kProducerThreads + 32;
+constexpr int kATileBytes = BM * BK * 2;       // 16 KB
+constexpr int kBBlockBytes = 64 * BK * 2;      // 8 KB per 64 columns of B
+constexpr uint32_t kSpinLimit = 1u << 28;
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > kSpinLimit) __trap();  // never hang the GPU: a protocol bug becomes an error
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;   // descriptor version (Blackwell)
+  d |= 2ull << 61;   // layout type SWIZZLE_128B
+  return d;
+}
+
+// fp32 x8 -> bf16 hi (and residual lo) packed as 16 bytes each
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    float r0 = v[2 * i] - __low2float(hb), r1 = v[2 * i + 1] - __high2float(hb);
+    __nv_bfloat162 lb = __floats2bfloat162_rn(r0, r1);
+    h[i] = *reinterpret_cast<uint32_t*>(&hb);
+    l[i] = *reinterpret_cast<uint32_t*>(&lb);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// Loads chunk `c` (8 fp32 values) of a [rows x 64k] operand tile.
+//  K-major source (MN == false): element (r, k) at P[r*ld + k]; chunk c -> row c/8, k-chunk c%8.
+//  MN-major source (MN == true): element (r, k) at P[k*ld + r]; chunk c -> k-row c/(rows/8), r-chunk c%(rows/8).
+template <bool MN>
+__device__ __forceinline__ void load_chunk(const float* __restrict__ P, int64_t ld, int rows_total, int k_end, int r0,
+                                           int k0, int c, int tile_rows, float* v) {
+  int r, k;
+  if (!MN) { r = r0 + (c >> 3); k = k0 + (c & 7) * 8; }
+  else { const int rc = tile_rows >> 3; k = k0 + c / rc; r = r0 + (c % rc) * 8; }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  if (!MN) {
+    if (r >= rows_total || k >= k_end) return;
+    const float* src = P + (int64_t)r * ld + k;
+    if (k + 8 <= k_end) {
+      float4 a = ld4(src), b = ld4(src + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+      for (int i = 0; i < 8; ++i) if (k + i < k_end) v[i] = src[i];
+    }
+  } else {
+    if (k >= k_end || r >= rows_total) return;
+    const float* src = P + (int64_t)k * ld + r;
+    if (r + 8 <= rows_total) {
+      float4 a = ld4(src), b = ld4(src + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+      for (int i = 0; i < 8; ++i) if (r + i < rows_total) v[i] = src[i];
+    }
+  }
+}
+
+// Byte offset of chunk `c` inside an operand tile stored in the canonical SWIZZLE_128B layout.
+//  K-major : rows of 128 B (64 bf16 of K), 8-row groups of 1024 B.
+//  MN-major: 64-column blocks of kBBlockBytes; inside a block 8-k-row groups of 1024 B, each k-row 128 B.
+template <bool MN>
+__device__ __forceinline__ uint32_t chunk_offset(int c, int tile_rows) {
+  if (!MN) {
+    const int r = c >> 3, ck = c & 7;
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((ck ^ (r & 7)) << 4));
+  }
+  const int rc = tile_rows >> 3;
+  const int k = c / rc, cm = c % rc;
+  const int blk = cm >> 3, cc = cm & 7;
+  return (uint32_t)(blk * kBBlockBytes + (k >> 3) * 1024 + (k & 7) * 128 + ((cc ^ (k & 7)) << 4));
+}
+
+struct TcArgs {
+  GemmParams p;
+  int BN;          // tile width (multiple of 16, <= 256)
+  int nb_blocks;   // ceil(BN / 64)
+  int stages;
+  int kb_per_split;
+  int tmem_cols;
+};
+
+template <bool A_MN, bool B_MN, bool SPLIT>
+__global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const GemmParams& p = a.p;
+  // carve: [stage tiles ...][barriers]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int b_tile_bytes = a.nb_blocks * kBBlockBytes;
+  const int plane = SPLIT ? 2 : 1;
+  const int stage_bytes = plane * (kATileBytes + b_tile_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
+  // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full ; then tmem base word ; then reduction scratch
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);  // 16 x 16 x 8 floats (bias-gradient partials)
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * a.BN;
+  const int nkb_total = (p.K + BK - 1) / BK;
+  const int kb_begin = blockIdx.z * a.kb_per_split;
+  const int kb_end = min(nkb_total, kb_begin + a.kb_per_split);
+  const int nkb = kb_end - kb_begin;
+
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(smem_u32(&bars[s]), kProducerThreads);
+      mbar_init(smem_u32(&bars[a.stages + s]), 1);
+    }
+    mbar_init(smem_u32(&bars[2 * a.stages]), 1);
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // =========================================================== MMA issuer
+    if (lane == 0 && nkb > 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(a.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t a_lbo = A_MN ? kBBlockBytes : 16, b_lbo = B_MN ? kBBlockBytes : 16;
+      const uint32_t a_kstep = A_MN ? 2048 : 32, b_kstep = B_MN ? 2048 : 32;
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % a.stages;
+        const uint32_t ph = (uint32_t)(i / a.stages) & 1u;
+        mbar_wait(smem_u32(&bars[s]), ph);
+        tc_fence_after();
+        const uint32_t sa_hi = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t sb_hi = sa_hi + plane * kATileBytes;
+        const uint32_t sa_lo = sa_hi + kATileBytes;
+        const uint32_t sb_lo = sb_hi + b_tile_bytes;
+#pragma unroll
+        for (int kk = 0; kk < BK / 16; ++kk) {
+          const uint64_t da_hi = make_desc(sa_hi + kk * a_kstep, a_lbo, 1024);
+          const uint64_t db_hi = make_desc(sb_hi + kk * b_kstep, b_lbo, 1024);
+          if (SPLIT) {
+            const uint64_t da_lo = make_desc(sa_lo + kk * a_kstep, a_lbo, 1024);
+            const uint64_t db_lo = make_desc(sb_lo + kk * b_kstep, b_lbo, 1024);
+            umma_bf16(tmem_base, da_lo, db_hi, idesc, (i | kk) != 0);
+            umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
+            umma_bf16(tmem_base, da_hi, db_hi, idesc, 1u);
+          } else {
+            umma_bf16(tmem_base, da_hi, db_hi, idesc, (i | kk) != 0);
+          }
+        }
+        umma_commit(smem_u32(&bars[a.stages + s]));  // frees the smem stage once these MMAs retire
+      }
+      umma_commit(smem_u32(&bars[2 * a.stages]));    // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // =========================================================== operand producers
+    const int b_rows = a.nb_blocks * 64;
+    const int nb_chunks = a.nb_blocks * 2;  // per thread: (nb_blocks*64 rows * 8 chunks) / 256
+    float csum[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) csum[e] = 0.f;
+    const bool do_colsum = A_MN && p.colsum_a != nullptr && blockIdx.x == 0;
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % a.stages;
+      const uint32_t ph = (uint32_t)(i / a.stages) & 1u;
+      const int k0 = (kb_begin + i) * BK;
+      const int k_end = min(p.K, kb_end * BK);
+      float va[4][8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) load_chunk<A_MN>(p.A, p.lda, p.M, k_end, m0, k0, tid + j * kProducerThreads, BM, va[j]);
+      float vb[8][8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nb_chunks) load_chunk<B_MN>(p.B, p.ldb, p.N, k_end, n0, k0, tid + j * kProducerThreads, b_rows, vb[j]);
+      if (do_colsum) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int e = 0; e < 8; ++e) csum[e] += va[j][e];
+      }
+      mbar_wait(smem_u32(&bars[a.stages + s]), ph ^ 1u);   // slot free (first pass returns at once)
+      uint8_t* st = smem + (size_t)s * stage_bytes;
+      uint8_t* sa_hi = st;
+      uint8_t* sa_lo = st + kATileBytes;
+      uint8_t* sb_hi = st + plane * kATileBytes;
+      uint8_t* sb_lo = sb_hi + b_tile_bytes;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 hi, lo;
+        split8(va[j], hi, lo);
+        const uint32_t off = chunk_offset<A_MN>(tid + j * kProducerThreads, BM);
+        *reinterpret_cast<uint4*>(sa_hi + off) = hi;
+        if (SPLIT) *reinterpret_cast<uint4*>(sa_lo + off) = lo;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nb_chunks) {
+          uint4 hi, lo;
+          split8(vb[j], hi, lo);
+          const uint32_t off = chunk_offset<B_MN>(tid + j * kProducerThreads, b_rows);
+          *reinterpret_cast<uint4*>(sb_hi + off) = hi;
+          if (SPLIT) *reinterpret_cast<uint4*>(sb_lo + off) = lo;
+        }
+      fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      mbar_arrive(smem_u32(&bars[s]));
+    }
+
+    // bias gradient: thread t always owns MN chunk (t % 16) of A^T -> reduce the 16 owners in smem
+    if (do_colsum) {
+      const int cm = tid & 15, owner = tid >> 4;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) red[(owner * 16 + cm) * 8 + e] = csum[e];
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (do_colsum && tid < 128) {
+      const int cm = tid >> 3, e = tid & 7;
+      float tot = 0.f;
+#pragma unroll
+      for (int o = 0; o < 16; ++o) tot += red[(o * 16 + cm) * 8 + e];
+      const int gm = m0 + cm * 8 + e;
+      if (gm < p.M) atomicAdd(&p.colsum_a[gm], tot);
+    }
+
+    // =========================================================== epilogue
+    if (nkb > 0) {
+      mbar_wait(smem_u32(&bars[2 * a.stages]), 0u);
+      tc_fence_after();
+    }
+    const int q = warp & 3, half = warp >> 2;
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const int nchunks = a.BN >> 4;
+    for (int c = half; c < nchunks; c += 2) {
+      const int gn = n0 + c * 16;
+      if (gn >= p.N) break;
+      float v[16];
+      if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), v);
+      else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+      }
+      const bool full = gn + 16 <= p.N;   // N % 4 == 0 is guaranteed by the dispatcher
+      if (p.splitk > 1) {
+        if (row_ok) {
+          float* dst = p.C + (int64_t)row * p.ldc + gn;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (full || gn + j < p.N) atomicAdd(dst + j, v[j]);
+        }
+        continue;
+      }
+#pragma unroll
+      for (int g4 = 0; g4 < 4; ++g4) {
+        const int col = gn + g4 * 4;
+        const bool ok = row_ok && col < p.N;
+        float* w = v + g4 * 4;
+        if (p.bias && col < p.N) {
+          float4 b = ld4(p.bias + col);
+          w[0] += b.x; w[1] += b.y; w[2] += b.z; w[3] += b.w;
+        }
+        if (ok && p.C_pre) st4(p.C_pre + (int64_t)row * p.ldpre + col, make_float4(w[0], w[1], w[2], w[3]));
+        if (p.act >= 0) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w[j] = act_fwd_rt(p.act, w[j]);
+        }
+        if (ok && p.mask_src) {
+          float4 ms = ld4(p.mask_src + (int64_t)row * p.ldmask + col);
+          float mv[4] = {ms.x, ms.y, ms.z, ms.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) w[j] *= p.mask_is_post ? (mv[j] > 0.f ? 1.f : 0.f) : act_bwd_rt(p.mask_act, mv[j]);
+        }
+        if (ok && p.p_drop > 0.f) {
+          float4 sc = dropout_scale4(p.p_drop, p.seed, p.offset, p.site, ((uint64_t)row * (uint64_t)p.N + col) >> 2);
+          w[0] *= sc.x; w[1] *= sc.y; w[2] *= sc.z; w[3] *= sc.w;
+        }
+        if (ok && p.R1) {
+          float4 r = ld4(p.R1 + (int64_t)row * p.ldr1 + col);
+          w[0] += r.x; w[1] += r.y; w[2] += r.z; w[3] += r.w;
+        }
+        if (ok && p.R2) {
+          float4 r = ld4(p.R2 + (int64_t)row * p.ldr2 + col);
+          w[0] += r.x; w[1] += r.y; w[2] += r.z; w[3] += r.w;
+        }
+        if (ok) st4(p.C + (int64_t)row * p.ldc + col, make_float4(w[0], w[1], w[2], w[3]));
+        if (!ok) { w[0] = w[1] = w[2] = w[3] = 0.f; }
+      }
+      if (p.stats) {
+        // column sums over the warp's 32 rows: butterfly reduce-scatter, 16 columns x {sum, sumsq}
+        float s1[16], s2[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { s1[j] = v[j]; s2[j] = v[j] * v[j]; }
+        // step xor 16: lanes < 16 keep columns 0-7, lanes >= 16 keep columns 8-15
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool up = (lane & 16) != 0;
+          float send1 = up ? s1[j] : s1[j + 8], send2 = up ? s2[j] : s2[j + 8];
+          float keep1 = up ? s1[j + 8] : s1[j], keep2 = up ? s2[j + 8] : s2[j];
+          s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 16);
+          s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool up = (lane & 8) != 0;
+          float send1 = up ? s1[j] : s1[j + 4], send2 = up ? s2[j] : s2[j + 4];
+          float keep1 = up ? s1[j + 4] : s1[j], keep2 = up ? s2[j + 4] : s2[j];
+          s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 8);
+          s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const bool up = (lane & 4) != 0;
+          float send1 = up ? s1[j] : s1[j + 2], send2 = up ? s2[j] : s2[j + 2];
+          float keep1 = up ? s1[j + 2] : s1[j], keep2 = up ? s2[j + 2] : s2[j];
+          s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 4);
+          s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 4);
+        }
+        {
+          const bool up = (lane & 2) != 0;
+          float send1 = up ? s1[0] : s1[1], send2 = up ? s2[0] : s2[1];
+          float keep1 = up ? s1[1] : s1[0], keep2 = up ? s2[1] : s2[0];
+          s1[0] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 2);
+          s2[0] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 2);
+        }
+        s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
+        s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
+        // lane owns column: bit4 -> +8, bit3 -> +4, bit2 -> +2, bit1 -> +1 ; lanes with bit0 == 0 write
+        const int colj = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+        if ((lane & 1) == 0 && gn + colj < p.N) {
+          atomic_add_f64(&p.stats[gn + colj], (double)s1[0]);
+          atomic_add_f64(&p.stats[(int64_t)p.N + gn + colj], (double)s2[0]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 8) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+}
+
+inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
+
+template <bool A_MN, bool B_MN, bool SPLIT>
+int launch(const TcArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    GPS_CUDA(cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  k_gemm_tc<A_MN, B_MN, SPLIT><<<grid, kThreads, smem, stream>>>(a);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+}  // namespace
+
+int gemm_tc(const GemmParams& p, cudaStream_t stream) {
+  static const int mode = [] {
+    const char* e = getenv("GPS_B200_TC");
+    return e ? atoi(e) : 3;   // bit0: K-major operands, bit1: MN-major operands
+  }();
+  if (p.M <= 0 || p.N <= 0) return GPS_OK;
+  if (p.K <= 0) return GPS_ERR_UNSUPPORTED;
+  const bool any_mn = p.ta || p.tb;
+  if (!(mode & 1)) return GPS_ERR_UNSUPPORTED;
+  if (any_mn && !(mode & 2)) return GPS_ERR_UNSUPPORTED;
+  // 128-bit paths: aligned bases, leading dimensions and N multiples of 4
+  if (!aligned16(p.A) || !aligned16(p.B) || !aligned16(p.C) || p.lda % 4 || p.ldb % 4 || p.ldc % 4 || p.N % 4)
+    return GPS_ERR_UNSUPPORTED;
+  if ((p.bias && !aligned16(p.bias)) || (p.R1 && (!aligned16(p.R1) || p.ldr1 % 4)) ||
+      (p.R2 && (!aligned16(p.R2) || p.ldr2 % 4)) || (p.mask_src && (!aligned16(p.mask_src) || p.ldmask % 4)) ||
+      (p.C_pre && (!aligned16(p.C_pre) || p.ldpre % 4)))
+    return GPS_ERR_UNSUPPORTED;
+  if (p.splitk > 1 && (p.bias || p.act >= 0 || p.mask_src || p.R1 || p.R2 || p.stats || p.C_pre || p.p_drop != 0.f)) {
+    set_error("gemm: split-K supports the plain product only");
+    return GPS_ERR_ARG;
+  }
+  if (p.colsum_a && !p.ta) {
+    set_error("gemm: colsum_a needs ta == 1");
+    return GPS_ERR_ARG;
+  }
+  const bool split = p.precision == GPS_PREC_FP32;
+  const int plane = split ? 2 : 1;
+  const int mt = (int)ceil_div(p.M, BM);
+  const int nkb = (int)ceil_div(p.K, BK);
+
+  // tile width: minimise waves x (bytes staged per tile), prefer wider tiles on ties
+  const int cands[6] = {256, 192, 160, 128, 96, 64};
+  int bestBN = 128;
+  long bestCost = -1;
+  for (int ci = 0; ci < 6; ++ci) {
+    int bn = cands[ci];
+    if (bn > (int)round_up(p.N, 16)) bn = (int)round_up(p.N, 16);
+    long tiles = (long)mt * ceil_div(p.N, bn) * (p.splitk > 1 ? p.splitk : 1);
+    long waves = ceil_div(tiles, kNumSMs);
+    long cost = waves * (BM + (long)ceil_div(bn, 64) * 64);
+    if (bestCost < 0 || cost < bestCost) { bestCost = cost; bestBN = bn; }
+  }
+  TcArgs a;
+  a.p = p;
+  a.BN = bestBN;
+  a.nb_blocks = (int)ceil_div(a.BN, 64);
+  const int stage_bytes = plane * (kATileBytes + a.nb_blocks * kBBlockBytes);
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages < 2) return GPS_ERR_UNSUPPORTED;
+  if (stages > nkb) stages = nkb < 2 ? 2 : nkb;
+  a.stages = stages;
+  int splitk = p.splitk > 1 ? p.splitk : 1;
+  if (splitk > nkb) splitk = nkb;
+  a.kb_per_split = (int)ceil_div(nkb, splitk);
+  splitk = (int)ceil_div(nkb, a.kb_per_split);
+  a.p.splitk = p.splitk > 1 ? 2 : 1;   // "accumulate atomically" flag
+  a.tmem_cols = a.BN <= 32 ? 32 : a.BN <= 64 ? 64 : a.BN <= 128 ? 128 : 256;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 1) * 8 + 16 + 16 * 16 * 8 * 4;
+  dim3 grid((unsigned)ceil_div(p.N, a.BN), (unsigned)mt, (unsigned)splitk);
+  const bool amn = p.ta != 0, bmn = p.tb != 0;
+#define GPS_TC_CASE(AM, BMN)                                                        \
+  if (amn == AM && bmn == BMN)                                                      \
+    return split ? launch<AM, BMN, true>(a, grid, smem, stream) : launch<AM, BMN, false>(a, grid, smem, stream);
+  GPS_TC_CASE(false, false)
+  GPS_TC_CASE(false, true)
+  GPS_TC_CASE(true, false)
+  GPS_TC_CASE(true, true)
+#undef GPS_TC_CASE
+  return GPS_ERR_UNSUPPORTED;
+}
+
 }  // namespace gps

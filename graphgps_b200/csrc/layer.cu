@@ -654,6 +654,22 @@ extern "C" int gps_linear_forward(const float* A, int64_t lda, const float* W, i
   return gemm(g, (cudaStream_t)stream);
 }
 
+extern "C" int gps_gemm(const float* A, int64_t lda, int32_t ta, const float* B, int64_t ldb, int32_t tb, float* C,
+                        int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t splitk, int32_t precision, int32_t impl,
+                        void* stream) {
+  GemmParams g;
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.A = A; g.lda = (int)lda; g.ta = ta; g.B = B; g.ldb = (int)ldb; g.tb = tb; g.C = C; g.ldc = (int)ldc;
+  g.splitk = splitk < 1 ? 1 : splitk; g.precision = precision;
+  if (impl == 1) return gemm_simt(g, (cudaStream_t)stream);
+  if (impl == 2) {
+    int rc = gemm_tc(g, (cudaStream_t)stream);
+    if (rc == GPS_ERR_UNSUPPORTED) set_error("gps_gemm: the tcgen05 kernel does not take this shape/alignment");
+    return rc;
+  }
+  return gemm(g, (cudaStream_t)stream);
+}
+
 extern "C" int gps_gatedgcn_aggregate_forward(const GpsGraph* g, int64_t d, const float* Ax, const float* Bx,
                                               const float* Dx, const float* Ex, int64_t ldy, float* Ce, float* xt,
                                               double* stats_x, double* stats_e, void* stream) {

@@ -177,6 +177,16 @@ int gps_linear_forward(const float* A, int64_t lda, const float* W, int64_t ldw,
                        float* C, int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t act,
                        int32_t precision, void* stream);
 
+/* General dense product used for the data / weight gradients of every Linear:
+ *   C[M,N] (+)= Aop[M,K] * Bop[K,N];  ta==0: Aop[m,k]=A[m*lda+k], ta==1: Aop[m,k]=A[k*lda+m];
+ *   tb==0: Bop[k,n]=B[n*ldb+k] (an nn.Linear weight), tb==1: Bop[k,n]=B[k*ldb+n].
+ * splitk > 1 accumulates atomically into a pre-zeroed C.  impl: 0 = dispatcher (tcgen05 when the
+ * shape qualifies), 1 = exact CUDA-core kernel, 2 = tcgen05 kernel (GPS_ERR_UNSUPPORTED if it does
+ * not take the shape). */
+int gps_gemm(const float* A, int64_t lda, int32_t ta, const float* B, int64_t ldb, int32_t tb, float* C,
+             int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t splitk, int32_t precision, int32_t impl,
+             void* stream);
+
 /* GatedGCN message+aggregate+update (gatedgcn_layer.py:90-136) given the five projections.
  * Y holds [Ax | Bx | Dx | Ex] columns at the given offsets with row stride ldy; Ce [E,d] is
  * overwritten with e_ij (pre-activation edge output, :106,:134); xt [N,d] = Ax + num/(den+1e-6).
