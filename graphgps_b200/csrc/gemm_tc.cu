@@ -5,18 +5,19 @@
 //   fp32 accumulation in TMEM.  precision FP32: split-bf16 x3 (hi*hi + hi*lo + lo*hi, ~2^-16
 //   relative), precision BF16: a single bf16 pass.
 //
-// Structure (one 128 x BN output tile per CTA, BN a runtime multiple of 16 up to 256):
-//   * warps 0-7 (256 threads) stage operands: coalesced 128-bit global loads of the fp32 tiles ->
+// Structure (one 128 x BN output tile per CTA, BN a runtime multiple of 16 up to 128):
+//   * warps 0-15 (512 threads) stage operands (register double-buffered: the global loads of k-block
+//     i+1 are in flight while k-block i is converted): coalesced 128-bit global loads of the fp32 tiles ->
 //     bf16 hi/lo split in registers -> 16-byte st.shared into the canonical UMMA SWIZZLE_128B
 //     layout (K-major when the reduction dim is contiguous in HBM, MN-major when it is the row
 //     dim, e.g. weight gradients dW = G^T X) -> fence.proxy.async -> mbarrier arrive.
 //     No transposes, no separate conversion pass, and the fp32->bf16 split costs no extra HBM bytes.
-//   * warp 8: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16) per
+//   * warp 16: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16) per
 //     16-wide K step, tcgen05.commit releases the smem stage / signals the epilogue.
-//   * epilogue (warps 0-7): tcgen05.ld 32x32b.x16 -> bias / activation / act' mask / dropout /
+//   * epilogue (warps 0-15): tcgen05.ld 32x32b.x16 -> bias / activation / act' mask / dropout /
 //     residuals / 128-bit stores; BatchNorm column sums by a warp butterfly reduce-scatter + double
 //     atomics; split-K partials by fp32 atomics.
-// Smem stages form an mbarrier ring (full: 256 producer arrivals; empty: tcgen05.commit).
+// Smem stages form an mbarrier ring (full: 512 producer arrivals; empty: tcgen05.commit).
 #include <cuda_bf16.h>
 
 #include "gemm.cuh"
@@ -27,7 +28,8 @@ namespace {
 
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 64;           // k-block: one 128-byte swizzle row of bf16
-constexpr int kProducerThreads = 256;
+constexpr int kProducerThreads = 512;      // 16 producer/epilogue warps
+constexpr int kMmaWarp = kProducerThreads / 32;
 constexpr int kThreads = kProducerThreads + 32;
 constexpr int kATileBytes = BM * BK * 2;       // 16 KB
 constexpr int kBBlockBytes = 64 * BK * 2;      // 8 KB per 64 columns of B
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
   // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full ; then tmem base word ; then reduction scratch
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
-  float* red = reinterpret_cast<float*>(tmem_slot + 2);  // 16 x 16 x 8 floats (bias-gradient partials)
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);  // 32 x 16 x 8 floats (bias-gradient partials)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * a.BN;
@@ -203,13 +205,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
     mbar_init(smem_u32(&bars[2 * a.stages]), 1);
     fence_barrier_init();
   }
-  if (warp == 8) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
+  if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == kMmaWarp) {
     // =========================================================== MMA issuer
     if (lane == 0 && nkb > 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
@@ -247,26 +249,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
   } else {
     // =========================================================== operand producers
     const int b_rows = a.nb_blocks * 64;
-    const int nb_chunks = a.nb_blocks * 2;  // per thread: (nb_blocks*64 rows * 8 chunks) / 256
+    const int nb_chunks = a.nb_blocks;      // per thread: (nb_blocks*64 rows * 8 chunks) / 512
     float csum[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) csum[e] = 0.f;
     const bool do_colsum = A_MN && p.colsum_a != nullptr && blockIdx.x == 0;
-    for (int i = 0; i < nkb; ++i) {
+    const int k_end = min(p.K, kb_end * BK);
+    float va0[2][8], va1[2][8], vb0[2][8], vb1[2][8];   // two register sets: k-block i and i+1
+
+    auto load_kb = [&](int i, float (*va)[8], float (*vb)[8]) {
+      const int k0 = (kb_begin + i) * BK;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) load_chunk<A_MN>(p.A, p.lda, p.M, k_end, m0, k0, tid + j * kProducerThreads, BM, va[j]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (j < nb_chunks) load_chunk<B_MN>(p.B, p.ldb, p.N, k_end, n0, k0, tid + j * kProducerThreads, b_rows, vb[j]);
+    };
+    auto store_kb = [&](int i, float (*va)[8], float (*vb)[8]) {
       const int s = i % a.stages;
       const uint32_t ph = (uint32_t)(i / a.stages) & 1u;
-      const int k0 = (kb_begin + i) * BK;
-      const int k_end = min(p.K, kb_end * BK);
-      float va[4][8];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) load_chunk<A_MN>(p.A, p.lda, p.M, k_end, m0, k0, tid + j * kProducerThreads, BM, va[j]);
-      float vb[8][8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < nb_chunks) load_chunk<B_MN>(p.B, p.ldb, p.N, k_end, n0, k0, tid + j * kProducerThreads, b_rows, vb[j]);
       if (do_colsum) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int j = 0; j < 2; ++j)
 #pragma unroll
           for (int e = 0; e < 8; ++e) csum[e] += va[j][e];
       }
@@ -277,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
       uint8_t* sb_hi = st + plane * kATileBytes;
       uint8_t* sb_lo = sb_hi + b_tile_bytes;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < 2; ++j) {
         uint4 hi, lo;
         split8(va[j], hi, lo);
         const uint32_t off = chunk_offset<A_MN>(tid + j * kProducerThreads, BM);
@@ -285,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
         if (SPLIT) *reinterpret_cast<uint4*>(sa_lo + off) = lo;
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 2; ++j)
         if (j < nb_chunks) {
           uint4 hi, lo;
           split8(vb[j], hi, lo);
@@ -295,6 +299,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
         }
       fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(smem_u32(&bars[s]));
+    };
+
+    if (nkb > 0) load_kb(0, va0, vb0);
+    for (int i = 0; i < nkb; i += 2) {
+      if (i + 1 < nkb) load_kb(i + 1, va1, vb1);
+      store_kb(i, va0, vb0);
+      if (i + 1 < nkb) {
+        if (i + 2 < nkb) load_kb(i + 2, va0, vb0);
+        store_kb(i + 1, va1, vb1);
+      }
     }
 
     // bias gradient: thread t always owns MN chunk (t % 16) of A^T -> reduce the 16 owners in smem
@@ -303,12 +317,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) red[(owner * 16 + cm) * 8 + e] = csum[e];
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, 512;" ::: "memory");
     if (do_colsum && tid < 128) {
       const int cm = tid >> 3, e = tid & 7;
       float tot = 0.f;
 #pragma unroll
-      for (int o = 0; o < 16; ++o) tot += red[(o * 16 + cm) * 8 + e];
+      for (int o = 0; o < 32; ++o) tot += red[(o * 16 + cm) * 8 + e];
       const int gm = m0 + cm * 8 + e;
       if (gm < p.M) atomicAdd(&p.colsum_a[gm], tot);
     }
@@ -318,11 +332,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
       mbar_wait(smem_u32(&bars[2 * a.stages]), 0u);
       tc_fence_after();
     }
-    const int q = warp & 3, half = warp >> 2;
+    const int q = warp & 3, half = warp >> 2;   // 4 column groups x 4 lane quadrants
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < p.M;
     const int nchunks = a.BN >> 4;
-    for (int c = half; c < nchunks; c += 2) {
+    for (int c = half; c < nchunks; c += 4) {
       const int gn = n0 + c * 16;
       if (gn >= p.N) break;
       float v[16];
@@ -428,7 +442,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp == 8) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
 }
 
 inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
@@ -478,10 +492,10 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
   const int nkb = (int)ceil_div(p.K, BK);
 
   // tile width: minimise waves x (bytes staged per tile), prefer wider tiles on ties
-  const int cands[6] = {256, 192, 160, 128, 96, 64};
+  const int cands[3] = {128, 96, 64};   // <= 128: two B chunks per producer thread per k-block
   int bestBN = 128;
   long bestCost = -1;
-  for (int ci = 0; ci < 6; ++ci) {
+  for (int ci = 0; ci < 3; ++ci) {
     int bn = cands[ci];
     if (bn > (int)round_up(p.N, 16)) bn = (int)round_up(p.N, 16);
     long tiles = (long)mt * ceil_div(p.N, bn) * (p.splitk > 1 ? p.splitk : 1);
@@ -505,7 +519,7 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
   splitk = (int)ceil_div(nkb, a.kb_per_split);
   a.p.splitk = p.splitk > 1 ? 2 : 1;   // "accumulate atomically" flag
   a.tmem_cols = a.BN <= 32 ? 32 : a.BN <= 64 ? 64 : a.BN <= 128 ? 128 : 256;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 1) * 8 + 16 + 16 * 16 * 8 * 4;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 1) * 8 + 16 + 32 * 16 * 8 * 4;
   dim3 grid((unsigned)ceil_div(p.N, a.BN), (unsigned)mt, (unsigned)splitk);
   const bool amn = p.ta != 0, bmn = p.tb != 0;
 #define GPS_TC_CASE(AM, BMN)                                                        \

@@ -53,21 +53,59 @@ def rel_err(a, b):
     return float((a - b).abs().max() / max(1.0, float(b.abs().max())))
 
 
-def compare(res, fix, tol, what=""):
-    errs = {}
-    for k in ("out_x", "out_e", "grad_x", "grad_e"):
+def rel_l2(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / max(float(b.norm()), 1e-30))
+
+
+def compare(res, fix, tol, what="", grad_l2_tol=None):
+    """Forward outputs and BatchNorm running statistics: max|a-b| / max(1, max|b|) <= tol.
+
+    Gradients: the same max-abs criterion, OR (when grad_l2_tol is given) relative L2 error
+    <= grad_l2_tol.  The second criterion exists because the derivative of a ReLU network is
+    discontinuous: a pre-activation within rounding distance of 0 flips its mask between two
+    correct arithmetics (the reference's own fp32 vs fp64 runs differ by 1.8e-2 max-abs on
+    ff_linear1.weight at the code2 shape for exactly this reason), which moves a handful of
+    gradient entries by O(|g|) while leaving the L2 error at the rounding level.  A real defect
+    (wrong operand, missing term) shows up as an L2 error of order 1.
+    """
+    errs, bad = {}, {}
+
+    def check_fwd(key, a, b):
+        e = rel_err(a, b)
+        errs[key] = e
+        if not e <= tol:
+            bad[key] = e
+
+    def check_grad(key, a, b):
+        e = rel_err(a, b)
+        errs[key] = e
+        if e <= tol:
+            return
+        if grad_l2_tol is not None:
+            l2 = rel_l2(a, b)
+            errs[key + "(l2)"] = l2
+            if l2 <= grad_l2_tol:
+                return
+            bad[key] = (e, l2)
+        else:
+            bad[key] = e
+
+    for k in ("out_x", "out_e"):
         if k in fix and k in res:
-            errs[k] = rel_err(res[k], fix[k])
+            check_fwd(k, res[k], fix[k])
+    for k in ("grad_x", "grad_e"):
+        if k in fix and k in res:
+            check_grad(k, res[k], fix[k])
     for n, g in fix.get("grad_params", {}).items():
         if n in res.get("grad_params", {}):
-            errs["grad:" + n] = rel_err(res["grad_params"][n], g)
+            check_grad("grad:" + n, res["grad_params"][n], g)
         else:
-            errs["grad:" + n] = float("inf")
+            bad["grad:" + n] = float("inf")
     for n, v in fix.get("state_after", {}).items():
         if v.is_floating_point():
-            errs["state:" + n] = rel_err(res["state_after"][n], v)
-        else:
-            errs["state:" + n] = float((res["state_after"][n] != v).any())
-    bad = {k: v for k, v in errs.items() if not v <= tol}
-    assert not bad, f"{what} tolerance {tol} exceeded: {bad}"
+            check_fwd("state:" + n, res["state_after"][n], v)
+        elif bool((res["state_after"][n] != v).any()):
+            bad["state:" + n] = 1.0
+    assert not bad, f"{what} tolerance {tol} (grad L2 {grad_l2_tol}) exceeded: {bad}"
     return errs
