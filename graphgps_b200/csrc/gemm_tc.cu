@@ -5,20 +5,26 @@
 //   fp32 accumulation in TMEM.  precision FP32: split-bf16 x3 (hi*hi + hi*lo + lo*hi, ~2^-16
 //   relative), precision BF16: a single bf16 pass.
 //
-// Structure (one 128 x BN output tile per CTA, BN a runtime multiple of 16 up to 128):
-//   * warps 0-15 (512 threads) stage operands (register double-buffered: the global loads of k-block
-//     i+1 are in flight while k-block i is converted): coalesced 128-bit global loads of the fp32 tiles ->
-//     bf16 hi/lo split in registers -> 16-byte st.shared into the canonical UMMA SWIZZLE_128B
-//     layout (K-major when the reduction dim is contiguous in HBM, MN-major when it is the row
-//     dim, e.g. weight gradients dW = G^T X) -> fence.proxy.async -> mbarrier arrive.
-//     No transposes, no separate conversion pass, and the fp32->bf16 split costs no extra HBM bytes.
-//   * warp 16: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16) per
-//     16-wide K step, tcgen05.commit releases the smem stage / signals the epilogue.
-//   * epilogue (warps 0-15): tcgen05.ld 32x32b.x16 -> bias / activation / act' mask / dropout /
+// One 128 x BN output tile per CTA (BN a runtime multiple of 16 up to 256; wide tiles matter: the kernel
+// is bound by L2->SM operand traffic, M*N*K*4*(1/BM + 1/BN) bytes):
+//   * warps 0-7 stage operands: coalesced 128-bit global loads of the fp32 tiles -> bf16 hi/lo split in
+//     registers -> 16-byte st.shared into the canonical UMMA SWIZZLE_128B layout (K-major when the
+//     reduction dim is contiguous in HBM, MN-major when it is the row dim, e.g. weight gradients
+//     dW = G^T X) -> fence.proxy.async -> one mbarrier arrive per warp.  All per-chunk addresses are
+//     (value for chunk 0) + q * constant, computed once per CTA.  No transposes, no separate conversion
+//     pass; the fp32->bf16 split costs no extra HBM bytes.
+//   * warp 8: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (UMMA 128 x BN x 16) per
+//     16-wide K step; tcgen05.commit releases the smem stage / signals the epilogue.
+//   * epilogue (warps 0-7): tcgen05.ld 32x32b.x16 -> bias / activation / act' mask / dropout /
 //     residuals / 128-bit stores; BatchNorm column sums by a warp butterfly reduce-scatter + double
-//     atomics; split-K partials by fp32 atomics.
-// Smem stages form an mbarrier ring (full: 512 producer arrivals; empty: tcgen05.commit).
+//     atomics; split-K partials by fp32 atomics; bias-gradient column sums from the staged A tile.
+// Smem stages form an mbarrier ring (full: one arrival per producer warp; empty: tcgen05.commit).
+// Measured lessons kept in the code: per-thread mbarrier arrivals (256 per stage) serialise on the
+// barrier unit (~1 us per k-block) -> per-warp arrivals; per-chunk integer divisions made the producers
+// issue-bound -> precomputed addressing (tools/gemm_triage.py has the switches and the clock64 trace).
 #include <cuda_bf16.h>
+
+#include <algorithm>
 
 #include "gemm.cuh"
 
@@ -28,9 +34,10 @@ namespace {
 
 constexpr int BM = 128;          // UMMA M
 constexpr int BK = 64;           // k-block: one 128-byte swizzle row of bf16
-constexpr int kProducerThreads = 512;      // 16 producer/epilogue warps
-constexpr int kMmaWarp = kProducerThreads / 32;
-constexpr int kThreads = kProducerThreads + 32;
+constexpr int kProducerWarps = 8;           // operand staging + epilogue
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kMmaWarp = kProducerWarps;
+constexpr int kThreads = (kMmaWarp + 1) * 32;
 constexpr int kATileBytes = BM * BK * 2;       // 16 KB
 constexpr int kBBlockBytes = 64 * BK * 2;      // 8 KB per 64 columns of B
 constexpr uint32_t kSpinLimit = 1u << 28;
@@ -174,21 +181,22 @@ struct TcArgs {
   int stages;
   int kb_per_split;
   int tmem_cols;
+  int debug;       // perf-triage switches (gps_debug_set): 1 no global loads, 2 no convert/store, 4 no MMA, 8 no epilogue
 };
 
 template <bool A_MN, bool B_MN, bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const GemmParams& p = a.p;
-  // carve: [stage tiles ...][barriers]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int b_tile_bytes = a.nb_blocks * kBBlockBytes;
   const int plane = SPLIT ? 2 : 1;
   const int stage_bytes = plane * (kATileBytes + b_tile_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)a.stages * stage_bytes);
-  // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full ; then tmem base word ; then reduction scratch
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * a.stages + 1);
-  float* red = reinterpret_cast<float*>(tmem_slot + 2);  // 32 x 16 x 8 floats (bias-gradient partials)
+  const int S = a.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_bytes);
+  // bars[0..S) full, bars[S..2S) empty, bars[2S] accumulator complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+  float* red = reinterpret_cast<float*>(tmem_slot + 2);  // 16 x 16 x 8 floats (bias-gradient partials)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * a.BN;
@@ -198,11 +206,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
   const int nkb = kb_end - kb_begin;
 
   if (tid == 0) {
-    for (int s = 0; s < a.stages; ++s) {
-      mbar_init(smem_u32(&bars[s]), kProducerThreads);
-      mbar_init(smem_u32(&bars[a.stages + s]), 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_u32(&bars[s]), kProducerWarps);
+      mbar_init(smem_u32(&bars[S + s]), 1);
     }
-    mbar_init(smem_u32(&bars[2 * a.stages]), 1);
+    mbar_init(smem_u32(&bars[2 * S]), 1);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(smem_u32(tmem_slot), (uint32_t)a.tmem_cols);
@@ -219,96 +227,122 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
       const uint32_t a_lbo = A_MN ? kBBlockBytes : 16, b_lbo = B_MN ? kBBlockBytes : 16;
       const uint32_t a_kstep = A_MN ? 2048 : 32, b_kstep = B_MN ? 2048 : 32;
       for (int i = 0; i < nkb; ++i) {
-        const int s = i % a.stages;
-        const uint32_t ph = (uint32_t)(i / a.stages) & 1u;
-        mbar_wait(smem_u32(&bars[s]), ph);
+        const int s = i % S;
+        mbar_wait(smem_u32(&bars[s]), (uint32_t)(i / S) & 1u);
         tc_fence_after();
         const uint32_t sa_hi = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t sb_hi = sa_hi + plane * kATileBytes;
         const uint32_t sa_lo = sa_hi + kATileBytes;
         const uint32_t sb_lo = sb_hi + b_tile_bytes;
+        if (!(a.debug & 4)) {
 #pragma unroll
-        for (int kk = 0; kk < BK / 16; ++kk) {
-          const uint64_t da_hi = make_desc(sa_hi + kk * a_kstep, a_lbo, 1024);
-          const uint64_t db_hi = make_desc(sb_hi + kk * b_kstep, b_lbo, 1024);
-          if (SPLIT) {
-            const uint64_t da_lo = make_desc(sa_lo + kk * a_kstep, a_lbo, 1024);
-            const uint64_t db_lo = make_desc(sb_lo + kk * b_kstep, b_lbo, 1024);
-            umma_bf16(tmem_base, da_lo, db_hi, idesc, (i | kk) != 0);
-            umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
-            umma_bf16(tmem_base, da_hi, db_hi, idesc, 1u);
-          } else {
-            umma_bf16(tmem_base, da_hi, db_hi, idesc, (i | kk) != 0);
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da_hi = make_desc(sa_hi + kk * a_kstep, a_lbo, 1024);
+            const uint64_t db_hi = make_desc(sb_hi + kk * b_kstep, b_lbo, 1024);
+            if (SPLIT) {
+              const uint64_t da_lo = make_desc(sa_lo + kk * a_kstep, a_lbo, 1024);
+              const uint64_t db_lo = make_desc(sb_lo + kk * b_kstep, b_lbo, 1024);
+              umma_bf16(tmem_base, da_lo, db_hi, idesc, (i | kk) != 0);
+              umma_bf16(tmem_base, da_hi, db_lo, idesc, 1u);
+              umma_bf16(tmem_base, da_hi, db_hi, idesc, 1u);
+            } else {
+              umma_bf16(tmem_base, da_hi, db_hi, idesc, (i | kk) != 0);
+            }
           }
         }
-        umma_commit(smem_u32(&bars[a.stages + s]));  // frees the smem stage once these MMAs retire
+        umma_commit(smem_u32(&bars[S + s]));  // frees the smem stage once these MMAs retire
       }
-      umma_commit(smem_u32(&bars[2 * a.stages]));    // accumulator complete
+      umma_commit(smem_u32(&bars[2 * S]));    // accumulator complete
     }
     __syncwarp();
   } else {
     // =========================================================== operand producers
+    // chunk c = tid + 256 q: every per-q quantity is (value at q = 0) + q * constant
+    //   K-major : row (tid>>3) + 32 q, k-chunk (tid&7)            -> global += 32 rows,   smem += 4096 B
+    //   MN-major: k-row (tid>>rcs) + (256>>rcs) q, row chunk tid & (rc-1) -> global += (256>>rcs) k-rows
     const int b_rows = a.nb_blocks * 64;
-    const int nb_chunks = a.nb_blocks;      // per thread: (nb_blocks*64 rows * 8 chunks) / 512
+    const int nb_chunks = a.nb_blocks * 2;  // per thread: (nb_blocks*64 rows * 8 chunks) / 256
+    const int a_rcs = 4;
+    const int b_rcs = a.nb_blocks == 1 ? 3 : a.nb_blocks == 2 ? 4 : 5;   // log2(b_rows / 8); nb_blocks in {1,2,4}
+    const int k_end = min(p.K, kb_end * BK);
+    const int64_t a_kstride = A_MN ? (int64_t)BK * p.lda : BK;   // floats per k-block
+    const int64_t b_kstride = B_MN ? (int64_t)BK * p.ldb : BK;
+    const int a_row0 = A_MN ? m0 + (tid & 15) * 8 : m0 + (tid >> 3);
+    const int a_k0 = A_MN ? (tid >> a_rcs) : (tid & 7) * 8;
+    const float* a_g0 = A_MN ? p.A + ((int64_t)kb_begin * BK + a_k0) * p.lda + a_row0
+                             : p.A + (int64_t)a_row0 * p.lda + (int64_t)kb_begin * BK + a_k0;
+    const int64_t a_gq = A_MN ? (int64_t)(kProducerThreads >> a_rcs) * p.lda : (int64_t)32 * p.lda;
+    const uint32_t a_s0 = chunk_offset<A_MN>(tid, BM);
+    const uint32_t a_sq = A_MN ? (uint32_t)((kProducerThreads >> a_rcs) / 8) * 1024u : 4096u;
+    const int b_row0 = B_MN ? n0 + (tid & ((1 << b_rcs) - 1)) * 8 : n0 + (tid >> 3);
+    const int b_k0 = B_MN ? (tid >> b_rcs) : (tid & 7) * 8;
+    const float* b_g0 = B_MN ? p.B + ((int64_t)kb_begin * BK + b_k0) * p.ldb + b_row0
+                             : p.B + (int64_t)b_row0 * p.ldb + (int64_t)kb_begin * BK + b_k0;
+    const int64_t b_gq = B_MN ? (int64_t)(kProducerThreads >> b_rcs) * p.ldb : (int64_t)32 * p.ldb;
+    const uint32_t b_s0 = chunk_offset<B_MN>(tid, b_rows);
+    const uint32_t b_sq = B_MN ? (uint32_t)((kProducerThreads >> b_rcs) / 8) * 1024u : 4096u;
     float csum[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) csum[e] = 0.f;
     const bool do_colsum = A_MN && p.colsum_a != nullptr && blockIdx.x == 0;
-    const int k_end = min(p.K, kb_end * BK);
-    float va0[2][8], va1[2][8], vb0[2][8], vb1[2][8];   // two register sets: k-block i and i+1
 
-    auto load_kb = [&](int i, float (*va)[8], float (*vb)[8]) {
-      const int k0 = (kb_begin + i) * BK;
+    for (int i = 0; i < nkb; ++i) {
+      const int s = i % S;
+      const uint32_t ph = (uint32_t)(i / S) & 1u;
+      const int krem = k_end - (kb_begin + i) * BK;     // valid k extent of this k-block (<= 64 on the tail)
+      float4 va[4][2], vb[8][2];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) load_chunk<A_MN>(p.A, p.lda, p.M, k_end, m0, k0, tid + j * kProducerThreads, BM, va[j]);
+      for (int q = 0; q < 4; ++q) {
+        const bool ok = !(a.debug & 1) && (A_MN ? (a_row0 < p.M && a_k0 + q * (kProducerThreads >> a_rcs) < krem)
+                                                : (a_row0 + 32 * q < p.M && a_k0 < krem));
+        const float* src = a_g0 + (int64_t)i * a_kstride + q * a_gq;
+        va[q][0] = ok ? ld4(src) : f4zero();
+        va[q][1] = ok ? ld4(src + 4) : f4zero();
+      }
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
-        if (j < nb_chunks) load_chunk<B_MN>(p.B, p.ldb, p.N, k_end, n0, k0, tid + j * kProducerThreads, b_rows, vb[j]);
-    };
-    auto store_kb = [&](int i, float (*va)[8], float (*vb)[8]) {
-      const int s = i % a.stages;
-      const uint32_t ph = (uint32_t)(i / a.stages) & 1u;
+      for (int q = 0; q < 8; ++q) {
+        const bool ok = !(a.debug & 1) && q < nb_chunks &&
+                        (B_MN ? (b_row0 < p.N && b_k0 + q * (kProducerThreads >> b_rcs) < krem)
+                              : (b_row0 + 32 * q < p.N && b_k0 < krem));
+        const float* src = b_g0 + (int64_t)i * b_kstride + q * b_gq;
+        vb[q][0] = ok ? ld4(src) : f4zero();
+        vb[q][1] = ok ? ld4(src + 4) : f4zero();
+      }
       if (do_colsum) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-#pragma unroll
-          for (int e = 0; e < 8; ++e) csum[e] += va[j][e];
+        for (int q = 0; q < 4; ++q) {
+          csum[0] += va[q][0].x; csum[1] += va[q][0].y; csum[2] += va[q][0].z; csum[3] += va[q][0].w;
+          csum[4] += va[q][1].x; csum[5] += va[q][1].y; csum[6] += va[q][1].z; csum[7] += va[q][1].w;
+        }
       }
-      mbar_wait(smem_u32(&bars[a.stages + s]), ph ^ 1u);   // slot free (first pass returns at once)
+      // one lane per warp polls / arrives: per-thread mbarrier traffic serialises on the barrier unit
+      if (lane == 0) mbar_wait(smem_u32(&bars[S + s]), ph ^ 1u);   // slot free (first pass returns at once)
+      __syncwarp();
       uint8_t* st = smem + (size_t)s * stage_bytes;
       uint8_t* sa_hi = st;
       uint8_t* sa_lo = st + kATileBytes;
       uint8_t* sb_hi = st + plane * kATileBytes;
       uint8_t* sb_lo = sb_hi + b_tile_bytes;
+      if (!(a.debug & 2)) {
 #pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        uint4 hi, lo;
-        split8(va[j], hi, lo);
-        const uint32_t off = chunk_offset<A_MN>(tid + j * kProducerThreads, BM);
-        *reinterpret_cast<uint4*>(sa_hi + off) = hi;
-        if (SPLIT) *reinterpret_cast<uint4*>(sa_lo + off) = lo;
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-        if (j < nb_chunks) {
+        for (int q = 0; q < 4; ++q) {
           uint4 hi, lo;
-          split8(vb[j], hi, lo);
-          const uint32_t off = chunk_offset<B_MN>(tid + j * kProducerThreads, b_rows);
-          *reinterpret_cast<uint4*>(sb_hi + off) = hi;
-          if (SPLIT) *reinterpret_cast<uint4*>(sb_lo + off) = lo;
+          split8(reinterpret_cast<const float*>(va[q]), hi, lo);
+          *reinterpret_cast<uint4*>(sa_hi + a_s0 + q * a_sq) = hi;
+          if (SPLIT) *reinterpret_cast<uint4*>(sa_lo + a_s0 + q * a_sq) = lo;
         }
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (q < nb_chunks) {
+            uint4 hi, lo;
+            split8(reinterpret_cast<const float*>(vb[q]), hi, lo);
+            *reinterpret_cast<uint4*>(sb_hi + b_s0 + q * b_sq) = hi;
+            if (SPLIT) *reinterpret_cast<uint4*>(sb_lo + b_s0 + q * b_sq) = lo;
+          }
+      } else if (va[0][0].x == 123.456f) { sa_hi[0] = (uint8_t)vb[0][0].x; }   // keep the loads alive
       fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-      mbar_arrive(smem_u32(&bars[s]));
-    };
-
-    if (nkb > 0) load_kb(0, va0, vb0);
-    for (int i = 0; i < nkb; i += 2) {
-      if (i + 1 < nkb) load_kb(i + 1, va1, vb1);
-      store_kb(i, va0, vb0);
-      if (i + 1 < nkb) {
-        if (i + 2 < nkb) load_kb(i + 2, va0, vb0);
-        store_kb(i + 1, va1, vb1);
-      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars[s]));
     }
 
     // bias gradient: thread t always owns MN chunk (t % 16) of A^T -> reduce the 16 owners in smem
@@ -317,125 +351,123 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
 #pragma unroll
       for (int e = 0; e < 8; ++e) red[(owner * 16 + cm) * 8 + e] = csum[e];
     }
-    asm volatile("bar.sync 1, 512;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     if (do_colsum && tid < 128) {
       const int cm = tid >> 3, e = tid & 7;
       float tot = 0.f;
 #pragma unroll
-      for (int o = 0; o < 32; ++o) tot += red[(o * 16 + cm) * 8 + e];
+      for (int o = 0; o < 16; ++o) tot += red[(o * 16 + cm) * 8 + e];
       const int gm = m0 + cm * 8 + e;
       if (gm < p.M) atomicAdd(&p.colsum_a[gm], tot);
     }
 
     // =========================================================== epilogue
     if (nkb > 0) {
-      mbar_wait(smem_u32(&bars[2 * a.stages]), 0u);
+      if (lane == 0) mbar_wait(smem_u32(&bars[2 * S]), 0u);
+      __syncwarp();
       tc_fence_after();
     }
-    const int q = warp & 3, half = warp >> 2;   // 4 column groups x 4 lane quadrants
+    const int q = warp & 3, half = warp >> 2;
     const int row = m0 + q * 32 + lane;
     const bool row_ok = row < p.M;
-    const int nchunks = a.BN >> 4;
-    for (int c = half; c < nchunks; c += 4) {
+    const int nchunks = (a.debug & 8) ? 0 : (a.BN >> 4);
+    for (int c = half; c < nchunks; c += 2) {
       const int gn = n0 + c * 16;
       if (gn >= p.N) break;
       float v[16];
       if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), v);
       else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = 0.f;
+        for (int e = 0; e < 16; ++e) v[e] = 0.f;
       }
-      const bool full = gn + 16 <= p.N;   // N % 4 == 0 is guaranteed by the dispatcher
-      if (p.splitk > 1) {
-        if (row_ok) {
-          float* dst = p.C + (int64_t)row * p.ldc + gn;
+        if (p.splitk > 1) {
+          if (row_ok) {
+            float* dst = p.C + (int64_t)row * p.ldc + gn;
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (full || gn + j < p.N) atomicAdd(dst + j, v[j]);
-        }
-        continue;
-      }
-#pragma unroll
-      for (int g4 = 0; g4 < 4; ++g4) {
-        const int col = gn + g4 * 4;
-        const bool ok = row_ok && col < p.N;
-        float* w = v + g4 * 4;
-        if (p.bias && col < p.N) {
-          float4 b = ld4(p.bias + col);
-          w[0] += b.x; w[1] += b.y; w[2] += b.z; w[3] += b.w;
-        }
-        if (ok && p.C_pre) st4(p.C_pre + (int64_t)row * p.ldpre + col, make_float4(w[0], w[1], w[2], w[3]));
-        if (p.act >= 0) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) w[j] = act_fwd_rt(p.act, w[j]);
-        }
-        if (ok && p.mask_src) {
-          float4 ms = ld4(p.mask_src + (int64_t)row * p.ldmask + col);
-          float mv[4] = {ms.x, ms.y, ms.z, ms.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) w[j] *= p.mask_is_post ? (mv[j] > 0.f ? 1.f : 0.f) : act_bwd_rt(p.mask_act, mv[j]);
-        }
-        if (ok && p.p_drop > 0.f) {
-          float4 sc = dropout_scale4(p.p_drop, p.seed, p.offset, p.site, ((uint64_t)row * (uint64_t)p.N + col) >> 2);
-          w[0] *= sc.x; w[1] *= sc.y; w[2] *= sc.z; w[3] *= sc.w;
-        }
-        if (ok && p.R1) {
-          float4 r = ld4(p.R1 + (int64_t)row * p.ldr1 + col);
-          w[0] += r.x; w[1] += r.y; w[2] += r.z; w[3] += r.w;
-        }
-        if (ok && p.R2) {
-          float4 r = ld4(p.R2 + (int64_t)row * p.ldr2 + col);
-          w[0] += r.x; w[1] += r.y; w[2] += r.z; w[3] += r.w;
-        }
-        if (ok) st4(p.C + (int64_t)row * p.ldc + col, make_float4(w[0], w[1], w[2], w[3]));
-        if (!ok) { w[0] = w[1] = w[2] = w[3] = 0.f; }
-      }
-      if (p.stats) {
-        // column sums over the warp's 32 rows: butterfly reduce-scatter, 16 columns x {sum, sumsq}
-        float s1[16], s2[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { s1[j] = v[j]; s2[j] = v[j] * v[j]; }
-        // step xor 16: lanes < 16 keep columns 0-7, lanes >= 16 keep columns 8-15
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const bool up = (lane & 16) != 0;
-          float send1 = up ? s1[j] : s1[j + 8], send2 = up ? s2[j] : s2[j + 8];
-          float keep1 = up ? s1[j + 8] : s1[j], keep2 = up ? s2[j + 8] : s2[j];
-          s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 16);
-          s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 16);
+            for (int e = 0; e < 16; ++e)
+              if (gn + e < p.N) atomicAdd(dst + e, v[e]);
+          }
+          continue;
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const bool up = (lane & 8) != 0;
-          float send1 = up ? s1[j] : s1[j + 4], send2 = up ? s2[j] : s2[j + 4];
-          float keep1 = up ? s1[j + 4] : s1[j], keep2 = up ? s2[j + 4] : s2[j];
-          s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 8);
-          s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 8);
-        }
+        for (int g4 = 0; g4 < 4; ++g4) {
+          const int col = gn + g4 * 4;
+          const bool ok = row_ok && col < p.N;
+          float* w = v + g4 * 4;
+          if (p.bias && col < p.N) {
+            float4 bb = ld4(p.bias + col);
+            w[0] += bb.x; w[1] += bb.y; w[2] += bb.z; w[3] += bb.w;
+          }
+          if (ok && p.C_pre) st4(p.C_pre + (int64_t)row * p.ldpre + col, make_float4(w[0], w[1], w[2], w[3]));
+          if (p.act >= 0) {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
-          const bool up = (lane & 4) != 0;
-          float send1 = up ? s1[j] : s1[j + 2], send2 = up ? s2[j] : s2[j + 2];
-          float keep1 = up ? s1[j + 2] : s1[j], keep2 = up ? s2[j + 2] : s2[j];
-          s1[j] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 4);
-          s2[j] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 4);
+            for (int e = 0; e < 4; ++e) w[e] = act_fwd_rt(p.act, w[e]);
+          }
+          if (ok && p.mask_src) {
+            float4 ms = ld4(p.mask_src + (int64_t)row * p.ldmask + col);
+            float mv[4] = {ms.x, ms.y, ms.z, ms.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) w[e] *= p.mask_is_post ? (mv[e] > 0.f ? 1.f : 0.f) : act_bwd_rt(p.mask_act, mv[e]);
+          }
+          if (ok && p.p_drop > 0.f) {
+            float4 sc = dropout_scale4(p.p_drop, p.seed, p.offset, p.site, ((uint64_t)row * (uint64_t)p.N + col) >> 2);
+            w[0] *= sc.x; w[1] *= sc.y; w[2] *= sc.z; w[3] *= sc.w;
+          }
+          if (ok && p.R1) {
+            float4 r = ld4(p.R1 + (int64_t)row * p.ldr1 + col);
+            w[0] += r.x; w[1] += r.y; w[2] += r.z; w[3] += r.w;
+          }
+          if (ok && p.R2) {
+            float4 r = ld4(p.R2 + (int64_t)row * p.ldr2 + col);
+            w[0] += r.x; w[1] += r.y; w[2] += r.z; w[3] += r.w;
+          }
+          if (ok) st4(p.C + (int64_t)row * p.ldc + col, make_float4(w[0], w[1], w[2], w[3]));
+          if (!ok) { w[0] = w[1] = w[2] = w[3] = 0.f; }
         }
-        {
-          const bool up = (lane & 2) != 0;
-          float send1 = up ? s1[0] : s1[1], send2 = up ? s2[0] : s2[1];
-          float keep1 = up ? s1[1] : s1[0], keep2 = up ? s2[1] : s2[0];
-          s1[0] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 2);
-          s2[0] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 2);
+        if (p.stats) {
+          // column sums over the warp's 32 rows: butterfly reduce-scatter, 16 columns x {sum, sumsq}
+          float s1[16], s2[16];
+#pragma unroll
+          for (int e = 0; e < 16; ++e) { s1[e] = v[e]; s2[e] = v[e] * v[e]; }
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const bool up = (lane & 16) != 0;
+            float send1 = up ? s1[e] : s1[e + 8], send2 = up ? s2[e] : s2[e + 8];
+            float keep1 = up ? s1[e + 8] : s1[e], keep2 = up ? s2[e + 8] : s2[e];
+            s1[e] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 16);
+            s2[e] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 16);
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const bool up = (lane & 8) != 0;
+            float send1 = up ? s1[e] : s1[e + 4], send2 = up ? s2[e] : s2[e + 4];
+            float keep1 = up ? s1[e + 4] : s1[e], keep2 = up ? s2[e + 4] : s2[e];
+            s1[e] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 8);
+            s2[e] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 8);
+          }
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const bool up = (lane & 4) != 0;
+            float send1 = up ? s1[e] : s1[e + 2], send2 = up ? s2[e] : s2[e + 2];
+            float keep1 = up ? s1[e + 2] : s1[e], keep2 = up ? s2[e + 2] : s2[e];
+            s1[e] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 4);
+            s2[e] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 4);
+          }
+          {
+            const bool up = (lane & 2) != 0;
+            float send1 = up ? s1[0] : s1[1], send2 = up ? s2[0] : s2[1];
+            float keep1 = up ? s1[1] : s1[0], keep2 = up ? s2[1] : s2[0];
+            s1[0] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 2);
+            s2[0] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 2);
+          }
+          s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
+          s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
+          const int colj = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+          if ((lane & 1) == 0 && gn + colj < p.N) {
+            atomic_add_f64(&p.stats[gn + colj], (double)s1[0]);
+            atomic_add_f64(&p.stats[(int64_t)p.N + gn + colj], (double)s2[0]);
+          }
         }
-        s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
-        s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
-        // lane owns column: bit4 -> +8, bit3 -> +4, bit2 -> +2, bit1 -> +1 ; lanes with bit0 == 0 write
-        const int colj = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-        if ((lane & 1) == 0 && gn + colj < p.N) {
-          atomic_add_f64(&p.stats[gn + colj], (double)s1[0]);
-          atomic_add_f64(&p.stats[(int64_t)p.N + gn + colj], (double)s2[0]);
-        }
-      }
     }
   }
 
@@ -444,6 +476,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
   tc_fence_after();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
 }
+
+int g_tc_debug = 0;
 
 inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
@@ -460,6 +494,9 @@ int launch(const TcArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
 }
 
 }  // namespace
+
+void gemm_tc_set_debug(int v) { g_tc_debug = v; }
+void gemm_tc_set_trace(long long*) {}
 
 int gemm_tc(const GemmParams& p, cudaStream_t stream) {
   static const int mode = [] {
@@ -478,6 +515,8 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
       (p.R2 && (!aligned16(p.R2) || p.ldr2 % 4)) || (p.mask_src && (!aligned16(p.mask_src) || p.ldmask % 4)) ||
       (p.C_pre && (!aligned16(p.C_pre) || p.ldpre % 4)))
     return GPS_ERR_UNSUPPORTED;
+  // lean producer loop: whole 8-element chunks are either inside or outside the operand
+  if ((!p.ta && p.K % 8) || (!p.tb && p.K % 8) || (p.ta && p.M % 8) || (p.tb && p.N % 8)) return GPS_ERR_UNSUPPORTED;
   if (p.splitk > 1 && (p.bias || p.act >= 0 || p.mask_src || p.R1 || p.R2 || p.stats || p.C_pre || p.p_drop != 0.f)) {
     set_error("gemm: split-K supports the plain product only");
     return GPS_ERR_ARG;
@@ -490,28 +529,30 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
   const int plane = split ? 2 : 1;
   const int mt = (int)ceil_div(p.M, BM);
   const int nkb = (int)ceil_div(p.K, BK);
+  const int splits_hint = p.splitk > 1 ? (p.splitk < nkb ? p.splitk : nkb) : 1;
 
-  // tile width: minimise waves x (bytes staged per tile), prefer wider tiles on ties
-  const int cands[3] = {128, 96, 64};   // <= 128: two B chunks per producer thread per k-block
+  // tile width: BN in {64,128,256}-block granularity (1, 2 or 4 staged 64-column blocks); the kernel is bound
+  // by operand traffic ~ tiles x (128 + staged B rows), so minimise waves x staged rows, wider on ties
   int bestBN = 128;
   long bestCost = -1;
-  for (int ci = 0; ci < 3; ++ci) {
-    int bn = cands[ci];
-    if (bn > (int)round_up(p.N, 16)) bn = (int)round_up(p.N, 16);
-    long tiles = (long)mt * ceil_div(p.N, bn) * (p.splitk > 1 ? p.splitk : 1);
+  for (int nt = (int)ceil_div(p.N, 256); nt <= (int)ceil_div(p.N, 48) + 1; ++nt) {
+    int bn = (int)round_up(ceil_div(p.N, nt), 16);
+    if (bn > 256) continue;
+    if (bn < 16) bn = 16;
+    int nb = bn <= 64 ? 1 : bn <= 128 ? 2 : 4;
+    long tiles = (long)mt * ceil_div(p.N, bn) * splits_hint;
     long waves = ceil_div(tiles, kNumSMs);
-    long cost = waves * (BM + (long)ceil_div(bn, 64) * 64);
+    long cost = waves * (BM + nb * 64L);
     if (bestCost < 0 || cost < bestCost) { bestCost = cost; bestBN = bn; }
   }
   TcArgs a;
   a.p = p;
   a.BN = bestBN;
-  a.nb_blocks = (int)ceil_div(a.BN, 64);
+  a.nb_blocks = a.BN <= 64 ? 1 : a.BN <= 128 ? 2 : 4;
   const int stage_bytes = plane * (kATileBytes + a.nb_blocks * kBBlockBytes);
   int stages = (200 * 1024) / stage_bytes;
   if (stages > 4) stages = 4;
   if (stages < 2) return GPS_ERR_UNSUPPORTED;
-  if (stages > nkb) stages = nkb < 2 ? 2 : nkb;
   a.stages = stages;
   int splitk = p.splitk > 1 ? p.splitk : 1;
   if (splitk > nkb) splitk = nkb;
@@ -519,7 +560,8 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
   splitk = (int)ceil_div(nkb, a.kb_per_split);
   a.p.splitk = p.splitk > 1 ? 2 : 1;   // "accumulate atomically" flag
   a.tmem_cols = a.BN <= 32 ? 32 : a.BN <= 64 ? 64 : a.BN <= 128 ? 128 : 256;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 1) * 8 + 16 + 32 * 16 * 8 * 4;
+  a.debug = g_tc_debug;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 1) * 8 + 16 + 16 * 16 * 8 * 4;
   dim3 grid((unsigned)ceil_div(p.N, a.BN), (unsigned)mt, (unsigned)splitk);
   const bool amn = p.ta != 0, bmn = p.tb != 0;
 #define GPS_TC_CASE(AM, BMN)                                                        \

@@ -621,6 +621,8 @@ extern "C" const char* gps_last_error(void) { return g_err; }
 extern "C" int gps_abi_version(void) { return GPS_ABI_VERSION; }
 extern "C" const char* gps_build_arch(void) { return "sm_100a"; }
 extern "C" unsigned long long gps_launch_count(void) { return g_launches.load(); }
+extern "C" void gps_debug_set(int v) { gemm_tc_set_debug(v); }
+extern "C" void gps_debug_trace(long long* p) { gemm_tc_set_trace(p); }  // perf-triage switches of the tcgen05 GEMM (tools/)
 
 extern "C" int gps_layer_plan(const GpsLayerArgs* args, GpsLayerPlan* plan) {
   GPS_REQUIRE(args && plan, GPS_ERR_ARG, "gps_layer_plan: null argument");
