@@ -219,7 +219,7 @@ def run_ours(args):
         from graphgps_b200.dp import allreduce_gradients
         grad_bucket = allreduce_gradients(params, grad_bucket)
 
-    def step(i, bobj=None):
+    def step(i, bobj=None, reduce=True):
         b = bobj if bobj is not None else dev_batches[i % NUM_BATCHES]
         ctx, cte = cts[i % NUM_BATCHES]
         bb = graphgps_b200.GraphBatch(x=b.x.detach().requires_grad_(True), edge_index=b.edge_index,
@@ -235,7 +235,8 @@ def run_ours(args):
             torch.autograd.backward([out.x, out.edge_attr], [ctx, cte])
         else:
             torch.autograd.backward([out.x], [ctx])
-        allreduce_grads()
+        if reduce:
+            allreduce_grads()
         return out, x_in
 
     def barrier():
@@ -244,29 +245,78 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing
-    for i in range(args.warmup):
+    # Eager warm-up (also sizes the shared workspace), then one CUDA graph per rotating batch: a replay
+    # re-executes the captured kernel sequence (forward + backward of the layer) with no host work.
+    for i in range(max(args.warmup, NUM_BATCHES)):
         step(i)
+    barrier()
+    graphs = None
+    launches_per_step = None
+    if args.graph:
+        graphs = []
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for i in range(NUM_BATCHES):
+                step(i, reduce=False)
+        torch.cuda.current_stream().wait_stream(side)
+        for i in range(NUM_BATCHES):
+            g = torch.cuda.CUDAGraph()
+            l0 = lib.gps_launch_count()
+            with torch.cuda.graph(g):
+                step(i, reduce=False)
+            launches_per_step = lib.gps_launch_count() - l0
+            graphs.append(g)
+
+    def run_step(i):
+        if graphs is None:
+            step(i)
+        else:
+            graphs[i % NUM_BATCHES].replay()
+            allreduce_grads()
+
+    for i in range(args.warmup):
+        run_step(i)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     evs = []
     l0 = lib.gps_launch_count()
+    host_t0 = time.perf_counter()
     for i in range(args.steps):
         flush.zero_()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        step(i)
+        run_step(i)
         e1.record()
         evs.append((e0, e1))
+    host_ms = (time.perf_counter() - host_t0) * 1e3 / args.steps   # host enqueue time per step (no sync inside)
     barrier()
-    launches = (lib.gps_launch_count() - l0) // max(1, args.steps)
+    launches = launches_per_step if graphs is not None else (lib.gps_launch_count() - l0) // max(1, args.steps)
     ms = sum(a.elapsed_time(b) for a, b in evs)
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
+
+    # eager (no CUDA graph) number for the same loop, reported alongside
+    eager_ms = None
+    if graphs is not None:
+        for i in range(3):
+            step(i)
+        barrier()
+        ee = []
+        for i in range(min(args.steps, 20)):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step(i)
+            e1.record()
+            ee.append((e0, e1))
+        barrier()
+        eager_ms = sum(a.elapsed_time(b) for a, b in ee) / len(ee)
 
     # ---------------- end-to-end through the public API with host buffers
     pinned = [b.clone().pin_memory() for b in cpu_batches]
@@ -323,7 +373,11 @@ def run_ours(args):
             "config": workload_config(args.workload, spec, local, glob, heads, drop, adrop, world),
             "e2e": {"value": e2e_value, "unit": "graphs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e_ms_total / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
+            "execution": ("CUDA graph replay (one captured fwd+bwd graph per rotating batch shape)" if args.graph
+                          else "eager launches"),
+            "eager": ({"ms_per_step": eager_ms, "value": B * world / (eager_ms * 1e-3)} if eager_ms else None),
+            "clocks": clocks, "roofline": roof,
             "cpu_baseline": {"value": cpu_value, "unit": "graphs/s", "cores": cores, "kind": kind,
                              "sample": f"{len(ct)} steps of one {B}-graph batch fwd+bwd (same workload), "
                                        f"torch fp32, {cores} threads"},
@@ -400,6 +454,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pcqm4m-small", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="time eager launches instead of CUDA-graph replays")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

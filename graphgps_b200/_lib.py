@@ -59,6 +59,7 @@ class GpsLayerArgs(C.Structure):
         ("grad_x_out", _fp), ("grad_edge_out", _fp), ("grad_x", _fp), ("grad_edge_attr", _fp),
         ("saved", _fp), ("saved_bytes", C.c_int64),
         ("workspace", _fp), ("workspace_bytes", C.c_int64),
+        ("offset_dev", _fp),
     ]
 
 

@@ -82,7 +82,11 @@ struct AttnArgs {
   float* lse; const float* lsec; float* delta; const float* deltac;
   float* dQ; float* dK; float* dV; int64_t ldg;
   float scale; float p_drop; uint64_t seed, offset;
+  const unsigned long long* offset_dev;
 };
+__device__ __forceinline__ uint64_t eff_offset(const AttnArgs& a) {
+  return a.offset + ((a.p_drop > 0.f && a.offset_dev) ? *a.offset_dev : 0ull);
+}
 
 template <int CH, int LPR>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_fwd(AttnArgs a) {
@@ -93,6 +97,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_fwd(AttnArgs a) {
   const int i = (blockIdx.x * kWarpsPerBlock + warp) * RPW + rloc;
   const bool row_ok = i < a.N;
   const int nch = a.hd / 4;
+  const uint64_t offs = eff_offset(a);
   int gs = 0, n = 0;
   if (row_ok) {
     int g = find_graph(a.gptr, a.B, i);
@@ -120,7 +125,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_fwd(AttnArgs a) {
     const float corr = (m_new == -INFINITY) ? 1.f : __expf(m - m_new);
     const float p = valid ? __expf(s - m_new) : 0.f;
     l = l * corr + p;
-    const float pd = p * drop_scale_pair(a.p_drop, a.seed, a.offset, h, i, jl);
+    const float pd = p * drop_scale_pair(a.p_drop, a.seed, offs, h, i, jl);
     load_slice<CH, LPR>(kv, a.V + (int64_t)j * a.ld + hoff, sub, nch, valid);
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -150,6 +155,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_q(AttnArgs a) 
   const int i = (blockIdx.x * kWarpsPerBlock + warp) * RPW + rloc;
   const bool row_ok = i < a.N;
   const int nch = a.hd / 4;
+  const uint64_t offs = eff_offset(a);
   int gs = 0, n = 0;
   if (row_ok) {
     int g = find_graph(a.gptr, a.B, i);
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_q(AttnArgs a) 
         dp += __shfl_xor_sync(0xffffffffu, dp, ofs);
       }
       const float p = valid ? __expf(s - lse) : 0.f;
-      const float ds = p * (dp * drop_scale_pair(a.p_drop, a.seed, a.offset, h, i, jl) - dl);
+      const float ds = p * (dp * drop_scale_pair(a.p_drop, a.seed, offs, h, i, jl) - dl);
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         gq[c].x += ds * kk[c].x;
@@ -213,6 +219,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_kv(AttnArgs a)
   const int j = (blockIdx.x * kWarpsPerBlock + warp) * RPW + rloc;
   const bool row_ok = j < a.N;
   const int nch = a.hd / 4;
+  const uint64_t offs = eff_offset(a);
   int gs = 0, n = 0;
   if (row_ok) {
     int g = find_graph(a.gptr, a.B, j);
@@ -246,7 +253,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_kv(AttnArgs a)
     const float lse = valid ? a.lsec[(int64_t)i * a.H + h] : 0.f;
     const float dl = valid ? a.deltac[(int64_t)i * a.H + h] : 0.f;
     const float p = valid ? __expf(s * a.scale - lse) : 0.f;
-    const float dsc = drop_scale_pair(a.p_drop, a.seed, a.offset, h, i, jl);
+    const float dsc = drop_scale_pair(a.p_drop, a.seed, offs, h, i, jl);
     const float pd = p * dsc;
     const float ds = p * (dp * dsc - dl) * a.scale;
 #pragma unroll
@@ -302,8 +309,9 @@ static int dispatch(int which, const AttnArgs& a, cudaStream_t stream) {
 
 int attention_fwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, const float* K, const float* V,
                   int64_t ld, float* O, int64_t ldo, float* lse, float p_drop, uint64_t seed, uint64_t offset,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const unsigned long long* offset_dev) {
   AttnArgs a{};
+  a.offset_dev = offset_dev;
   a.gptr = g.graph_ptr; a.B = (int)g.B; a.N = (int)g.N; a.H = (int)heads; a.hd = (int)hd;
   a.Q = Q; a.K = K; a.V = V; a.ld = ld; a.O = O; a.ldo = ldo; a.lse = lse;
   a.scale = 1.f / sqrtf((float)hd); a.p_drop = p_drop; a.seed = seed; a.offset = offset;
@@ -313,8 +321,9 @@ int attention_fwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, 
 int attention_bwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, const float* K, const float* V,
                   int64_t ld, const float* O, const float* dO, int64_t ldo, const float* lse, float* delta,
                   float* dQ, float* dK, float* dV, int64_t ldg, float p_drop, uint64_t seed, uint64_t offset,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const unsigned long long* offset_dev) {
   AttnArgs a{};
+  a.offset_dev = offset_dev;
   a.gptr = g.graph_ptr; a.B = (int)g.B; a.N = (int)g.N; a.H = (int)heads; a.hd = (int)hd;
   a.Q = Q; a.K = K; a.V = V; a.ld = ld; a.Oc = O; a.dO = dO; a.ldo = ldo; a.lsec = lse;
   a.delta = delta; a.deltac = delta; a.dQ = dQ; a.dK = dK; a.dV = dV; a.ldg = ldg;

@@ -96,7 +96,10 @@ struct OpBnActRes {
   const float* R; float* out; int64_t d;
   BnView bn; int act; DropCfg drop; double* stats;
   BnRegs reg;
-  __device__ void prepare(int c4) { reg.load(bn, c4); }
+  __device__ void prepare(int c4) {
+    reg.load(bn, c4);
+    if (drop.p > 0.f && drop.offset_dev) drop.offset += *drop.offset_dev;
+  }
   __device__ void row(int64_t r, int c4, float4* acc) {
     float4 v = act4(act, reg.apply(ld4(z + r * ldz + c4 * 4)));
     if (drop.p > 0.f)
@@ -146,7 +149,10 @@ struct OpBnBwdReduce {
   const float* g; int64_t ldg; const float* z; int64_t ldz; int64_t d;
   BnView bn; int act; DropCfg drop; double* sums;
   BnRegs reg;
-  __device__ void prepare(int c4) { reg.load(bn, c4); }
+  __device__ void prepare(int c4) {
+    reg.load(bn, c4);
+    if (drop.p > 0.f && drop.offset_dev) drop.offset += *drop.offset_dev;
+  }
   __device__ void row(int64_t r, int c4, float4* acc) {
     float4 zh = reg.zhat(ld4(z + r * ldz + c4 * 4));
     float4 gp = bn_bwd_gprime(g, ldg, r, c4, zh, reg, act, drop, d);
@@ -167,6 +173,7 @@ struct OpBnBwdApply {
   float4 s1raw, s2raw;
   __device__ void prepare(int c4) {
     reg.load(bn, c4);
+    if (drop.p > 0.f && drop.offset_dev) drop.offset += *drop.offset_dev;
     const double* a = sums + c4 * 4;
     const double* b = sums + d + c4 * 4;
     s1raw = make_float4((float)a[0], (float)a[1], (float)a[2], (float)a[3]);

@@ -142,7 +142,8 @@ __global__ void __launch_bounds__(NT) k_gemm_simt(GemmParams p, int kchunk, bool
     }
     if (p.p_drop > 0.f) {
       // gn is a multiple of 4 and ldc-independent: flat index over a dense [M, N] grid
-      float4 sc = dropout_scale4(p.p_drop, p.seed, p.offset, p.site, ((uint64_t)gm * (uint64_t)p.N + gn) >> 2);
+      float4 sc = dropout_scale4(p.p_drop, p.seed, p.offset + (p.offset_dev ? *p.offset_dev : 0ull), p.site,
+                                 ((uint64_t)gm * (uint64_t)p.N + gn) >> 2);
       v[0] *= sc.x; v[1] *= sc.y; v[2] *= sc.z; v[3] *= sc.w;
     }
     if (p.R1) {

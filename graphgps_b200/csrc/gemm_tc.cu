@@ -410,7 +410,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
             for (int e = 0; e < 4; ++e) w[e] *= p.mask_is_post ? (mv[e] > 0.f ? 1.f : 0.f) : act_bwd_rt(p.mask_act, mv[e]);
           }
           if (ok && p.p_drop > 0.f) {
-            float4 sc = dropout_scale4(p.p_drop, p.seed, p.offset, p.site, ((uint64_t)row * (uint64_t)p.N + col) >> 2);
+            float4 sc = dropout_scale4(p.p_drop, p.seed, p.offset + (p.offset_dev ? *p.offset_dev : 0ull), p.site,
+                                     ((uint64_t)row * (uint64_t)p.N + col) >> 2);
             w[0] *= sc.x; w[1] *= sc.y; w[2] *= sc.z; w[3] *= sc.w;
           }
           if (ok && p.R1) {

@@ -17,6 +17,7 @@ struct DropCfg {
   float p = 0.f;
   uint64_t seed = 0, offset = 0;
   int site = 0;
+  const unsigned long long* offset_dev = nullptr;  // optional device-resident addend (CUDA-graph replays)
 };
 
 // ---- BatchNorm statistics -----------------------------------------------------------------
@@ -75,10 +76,10 @@ int gine_bwd_src(const GpsGraph& g, int64_t d, const float* g_e, const float* g_
 // ---- attention ------------------------------------------------------------------------------
 int attention_fwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, const float* K, const float* V,
                   int64_t ld, float* O, int64_t ldo, float* lse, float p_drop, uint64_t seed, uint64_t offset,
-                  cudaStream_t stream);
+                  cudaStream_t stream, const unsigned long long* offset_dev = nullptr);
 int attention_bwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, const float* K, const float* V,
                   int64_t ld, const float* O, const float* dO, int64_t ldo, const float* lse, float* delta,
                   float* dQ, float* dK, float* dV, int64_t ldg, float p_drop, uint64_t seed, uint64_t offset,
-                  cudaStream_t stream);
+                  cudaStream_t stream, const unsigned long long* offset_dev = nullptr);
 
 }  // namespace gps

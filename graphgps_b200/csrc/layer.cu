@@ -316,6 +316,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
   auto drop = [&](int site) {
     DropCfg c;
     c.p = pd; c.seed = a->seed; c.offset = a->offset; c.site = site;
+    c.offset_dev = (const unsigned long long*)a->offset_dev;
     return c;
   };
   auto stats = [&](int which) -> double* { return train ? P.fstats + (int64_t)which * 2 * d : nullptr; };
@@ -364,6 +365,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g2.A = P.h1; g2.lda = (int)d; g2.B = a->gine_lin1.weight; g2.ldb = (int)d; g2.C = P.xloc; g2.ldc = (int)d;
     g2.bias = a->gine_lin1.bias; g2.R1 = a->x; g2.ldr1 = (int)d; g2.stats = stats(BN_L);
     g2.p_drop = pd; g2.seed = a->seed; g2.offset = a->offset; g2.site = GPS_SITE_LOCAL;
+    g2.offset_dev = (const unsigned long long*)a->offset_dev;
     g2.precision = a->precision;
     GPS_TRY(gemm(g2, st));
     GPS_TRY(bn_ready(P, a, BN_L, a->norm1_local, N, st));
@@ -372,12 +374,14 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
   // ---- global attention  (gps_layer.py:198-218, 234-241)
   if (P.attn) {
     const float* Q = P.Y1 + P.qkv_off;
-    GPS_TRY(attention_fwd(a->graph, P.H, P.hd, Q, Q + d, Q + 2 * d, P.Wy, P.O, d, P.lse, pa, a->seed, a->offset, st));
+    GPS_TRY(attention_fwd(a->graph, P.H, P.hd, Q, Q + d, Q + 2 * d, P.Wy, P.O, d, P.lse, pa, a->seed, a->offset, st,
+                          (const unsigned long long*)a->offset_dev));
     GemmParams g;  // hA = x + drop(O Wo^T + bo)
     g.M = (int)N; g.N = (int)d; g.K = (int)d;
     g.A = P.O; g.lda = (int)d; g.B = a->attn_out.weight; g.ldb = (int)d; g.C = P.hA; g.ldc = (int)d;
     g.bias = a->attn_out.bias; g.R1 = a->x; g.ldr1 = (int)d; g.stats = stats(BN_A);
     g.p_drop = pd; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_ATTN_OUT;
+    g.offset_dev = (const unsigned long long*)a->offset_dev;
     g.precision = a->precision;
     GPS_TRY(gemm(g, st));
     GPS_TRY(bn_ready(P, a, BN_A, a->norm1_attn, N, st));
@@ -400,12 +404,14 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.A = P.s; g.lda = (int)d; g.B = a->ff1.weight; g.ldb = (int)d; g.C = P.hid; g.ldc = (int)(2 * d);
     g.bias = a->ff1.bias; g.act = act; g.C_pre = P.hid_pre; g.ldpre = (int)(2 * d);
     g.p_drop = pd; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_FF1; g.precision = a->precision;
+    g.offset_dev = (const unsigned long long*)a->offset_dev;
     GPS_TRY(gemm(g, st));
     GemmParams g2;
     g2.M = (int)N; g2.N = (int)d; g2.K = (int)(2 * d);
     g2.A = P.hid; g2.lda = (int)(2 * d); g2.B = a->ff2.weight; g2.ldb = (int)(2 * d); g2.C = P.t; g2.ldc = (int)d;
     g2.bias = a->ff2.bias; g2.R1 = P.s; g2.ldr1 = (int)d; g2.stats = stats(BN_2);
     g2.p_drop = pd; g2.seed = a->seed; g2.offset = a->offset; g2.site = GPS_SITE_FF2; g2.precision = a->precision;
+    g2.offset_dev = (const unsigned long long*)a->offset_dev;
     GPS_TRY(gemm(g2, st));
     GPS_TRY(bn_ready(P, a, BN_2, a->norm2, N, st));
     GPS_TRY(bn_combine(P.t, bn_view(P, BN_2, a->norm2), nullptr, BnView(), a->x_out, N, d, st));  // :229
@@ -434,6 +440,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   auto drop = [&](int site) {
     DropCfg c;
     c.p = pd; c.seed = a->seed; c.offset = a->offset; c.site = site;
+    c.offset_dev = (const unsigned long long*)a->offset_dev;
     return c;
   };
   DropCfg nodrop;
@@ -459,6 +466,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     if (relu) { g.mask_src = P.hid; g.mask_is_post = 1; } else { g.mask_src = P.hid_pre; g.mask_act = act; }
     g.ldmask = (int)(2 * d);
     g.p_drop = pd; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_FF1; g.precision = prec;
+    g.offset_dev = (const unsigned long long*)a->offset_dev;
     GPS_TRY(gemm(g, st));
     GPS_TRY(linear_wgrad(g_ff2, d, P.hid, 2 * d, N, d, 2 * d, a->ff2.grad_weight, a->ff2.grad_bias, prec, st));
     GPS_TRY(linear_wgrad(P.g_hid, 2 * d, P.s, d, N, 2 * d, d, a->ff1.grad_weight, a->ff1.grad_bias, prec, st));
@@ -497,7 +505,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     const float* Q = P.Y1 + P.qkv_off;
     float* gQ = P.gY1 + P.qkv_off;
     GPS_TRY(attention_bwd(a->graph, P.H, P.hd, Q, Q + d, Q + 2 * d, P.Wy, P.O, P.g_O, d, P.lse, P.delta, gQ, gQ + d,
-                          gQ + 2 * d, P.Wy, pa, a->seed, a->offset, st));
+                          gQ + 2 * d, P.Wy, pa, a->seed, a->offset, st, (const unsigned long long*)a->offset_dev));
   }
 
   // ---- local model backward
@@ -587,7 +595,8 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
 // dedicated tiny kernel keeps it explicit.
 namespace {
 __global__ void k_dropmul(const float* __restrict__ src, float* __restrict__ dst, int64_t n4, int64_t c4n, float p,
-                          uint64_t seed, uint64_t offset, int site) {
+                          uint64_t seed, uint64_t offset, int site, const unsigned long long* offset_dev) {
+  if (offset_dev) offset += *offset_dev;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = ld4(src + i * 4);
     st4(dst + i * 4, f4mul(v, dropout_scale4(p, seed, offset, site, (uint64_t)i)));
@@ -607,7 +616,8 @@ static int dropmul(const float* src, float* dst, int64_t rows, int64_t d, const 
   int64_t n4 = rows * d / 4;
   if (n4 == 0) return GPS_OK;
   k_dropmul<<<(unsigned)std::min<int64_t>(ceil_div(n4, 256), kNumSMs * 8), 256, 0, st>>>(src, dst, n4, d / 4, a->dropout,
-                                                                                        a->seed, a->offset, site);
+                                                                                        a->seed, a->offset, site,
+                                                                                        (const unsigned long long*)a->offset_dev);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }

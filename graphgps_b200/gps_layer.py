@@ -28,6 +28,20 @@ _ACT_MODULES = {"relu": nn.ReLU, "gelu": nn.GELU}
 
 _workspaces = {}
 _dropout_calls = [0]
+_drop_counters = {}
+
+
+def _next_dropout_offset(device):
+    """Device-resident Philox offset for this call: counter += 4096; snapshot = counter.
+
+    Kept on the device (two tiny stream-ordered ops) so that a captured CUDA graph draws fresh dropout
+    masks on every replay; the snapshot tensor is what forward and backward of this call both read."""
+    ctr = _drop_counters.get(device)
+    if ctr is None:
+        ctr = torch.zeros(1, dtype=torch.int64, device=device)
+        _drop_counters[device] = ctr
+    ctr.add_(4096)
+    return ctr.clone()
 
 
 def _workspace(device, nbytes):
@@ -121,17 +135,20 @@ class _GPSLayerFn(torch.autograd.Function):
         N, E, d = gs.N, gs.E, layer.dim_h
         x_out = torch.empty_like(x)
         e_out = torch.empty_like(e) if layer.local_gnn_type == "CustomGatedGCN" else None
-        plan = _lib.GpsLayerPlan()
-        _lib.check(lib.gps_layer_plan(C.byref(args), C.byref(plan)), "gps_layer_plan")
-        saved = torch.empty(max(plan.saved_bytes, 256), dtype=torch.uint8, device=dev)
-        ws = _workspace(dev, max(plan.fwd_workspace_bytes, plan.bwd_workspace_bytes))
+        plan = layer._plan(args, gs)
+        saved = torch.empty(max(plan[0], 256), dtype=torch.uint8, device=dev)
+        ws = _workspace(dev, plan[1])
         args.x, args.edge_attr = x.data_ptr(), _lib.ptr(e)
         args.x_out, args.edge_out = x_out.data_ptr(), _lib.ptr(e_out)
         args.saved, args.saved_bytes = saved.data_ptr(), saved.numel()
         args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
+        snap = None
+        if layer.training and (layer.dropout > 0 or layer.attn_dropout > 0):
+            snap = _next_dropout_offset(dev)
+            args.offset, args.offset_dev = 0, snap.data_ptr()
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.gps_layer_forward(C.byref(args), stream), "gps_layer_forward")
-        ctx.layer, ctx.gs, ctx.saved_buf = layer, gs, saved
+        ctx.layer, ctx.gs, ctx.saved_buf, ctx.snap = layer, gs, saved, snap
         ctx.seed, ctx.offset, ctx.training = args.seed, args.offset, bool(args.training)
         ctx.save_for_backward(x, e, *params)
         if e_out is not None:
@@ -150,15 +167,16 @@ class _GPSLayerFn(torch.autograd.Function):
         grads = {n: torch.empty_like(p) for n, p in named.items()}
         args = layer._base_args(gs, named, grads)
         args.seed, args.offset, args.training = ctx.seed, ctx.offset, 1
+        if ctx.snap is not None:
+            args.offset_dev = ctx.snap.data_ptr()
         g_x_out = g_x_out.contiguous()
         gated = layer.local_gnn_type == "CustomGatedGCN"
         if g_e_out is not None:
             g_e_out = g_e_out.contiguous()
         g_x = torch.empty_like(x)
         g_e = torch.empty_like(e) if layer.local_gnn_type != "None" else None
-        plan = _lib.GpsLayerPlan()
-        _lib.check(lib.gps_layer_plan(C.byref(args), C.byref(plan)), "gps_layer_plan")
-        ws = _workspace(dev, max(plan.fwd_workspace_bytes, plan.bwd_workspace_bytes))
+        plan = layer._plan(args, gs)
+        ws = _workspace(dev, plan[1])
         args.x, args.edge_attr = x.data_ptr(), _lib.ptr(e)
         args.grad_x_out = g_x_out.data_ptr()
         args.grad_edge_out = _lib.ptr(g_e_out) if gated else 0
@@ -253,10 +271,48 @@ class GPSLayer(nn.Module):
         self.ff_linear2 = nn.Linear(dim_h * 2, dim_h)
         self.norm2 = nn.BatchNorm1d(dim_h)
         self._param_names = [n for n, _ in self.named_parameters()]
+        self._grad_shapes = [tuple(p.shape) for _, p in self.named_parameters()]
+        self._grad_sizes = [p.numel() for _, p in self.named_parameters()]
+        self._grad_numel = sum(self._grad_sizes)
+        self._plan_cache = {}
+
+    def _plan(self, args, gs):
+        """(saved_bytes, workspace_bytes) for this graph size; gps_layer_plan is pure in (config, N, E)."""
+        key = (gs.N, gs.E)
+        hit = self._plan_cache.get(key)
+        if hit is None:
+            plan = _lib.GpsLayerPlan()
+            _lib.check(_lib.load().gps_layer_plan(C.byref(args), C.byref(plan)), "gps_layer_plan")
+            hit = (int(plan.saved_bytes), int(max(plan.fwd_workspace_bytes, plan.bwd_workspace_bytes)))
+            if len(self._plan_cache) > 64:
+                self._plan_cache.clear()
+            self._plan_cache[key] = hit
+        return hit
 
     # ------------------------------------------------------------------------------------
     def _base_args(self, gs, named, grads=None):
-        """GpsLayerArgs with configuration, graph and parameter (+gradient) pointers filled in."""
+        """GpsLayerArgs with configuration, graph and parameter (+gradient) pointers filled in.
+
+        The forward-direction struct (no gradient pointers) only depends on the parameter addresses and the
+        module flags, so it is cached and copied; building ~30 nested ctypes structs per call costs more host
+        time than the GPU needs for the whole layer at the ZINC shape."""
+        if grads is None:
+            key = (tuple(t.data_ptr() for t in named.values()), self.training, self.precision,
+                   float(self.dropout), float(self.attn_dropout))
+            cached = self.__dict__.get("_args_cache")
+            if cached is None or cached[0] != key:
+                cached = (key, self._build_args(named, None))
+                self.__dict__["_args_cache"] = cached
+            a = _lib.GpsLayerArgs.from_buffer_copy(cached[1])
+        else:
+            a = self._build_args(named, grads)
+        a.seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        _dropout_calls[0] += 1
+        a.offset = _dropout_calls[0] * 4096
+        a.graph = gs.desc
+        return a
+
+    def _build_args(self, named, grads):
         g = grads or {}
         a = _lib.GpsLayerArgs()
         a.d, a.heads = self.dim_h, self.num_heads
@@ -266,10 +322,6 @@ class GPSLayer(nn.Module):
         a.training = 1 if self.training else 0
         a.precision = _lib.PRECISION[self.precision]
         a.dropout, a.attn_dropout = float(self.dropout), float(self.attn_dropout)
-        a.seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
-        _dropout_calls[0] += 1
-        a.offset = _dropout_calls[0] * 4096
-        a.graph = gs.desc
 
         def lin(prefix, bias=True):
             return _lin(named[prefix + ".weight"], named.get(prefix + ".bias") if bias else None,

@@ -151,6 +151,10 @@ typedef struct {
   /* caller-owned scratch; sizes from gps_layer_plan() */
   void* saved;   int64_t saved_bytes;     /* written by forward, read by backward   */
   void* workspace; int64_t workspace_bytes; /* transient; may be shared between calls on one stream */
+
+  /* optional device-resident addend for `offset` (uint64 on the device, read by the kernels at run time):
+   * lets a captured CUDA graph draw fresh dropout masks on every replay. NULL = use `offset` only. */
+  const uint64_t* offset_dev;
 } GpsLayerArgs;
 
 typedef struct {
@@ -205,6 +209,7 @@ int gps_gine_aggregate_forward(const GpsGraph* g, int64_t d, const float* x, con
 int gps_attention_forward(const GpsGraph* g, int64_t heads, int64_t hd, const float* Q,
                           const float* K, const float* V, int64_t ld, float* O, int64_t ldo,
                           float* lse, float p_drop, uint64_t seed, uint64_t offset, void* stream);
+/* (the layer-level calls additionally honour GpsLayerArgs.offset_dev) */
 int gps_attention_backward(const GpsGraph* g, int64_t heads, int64_t hd, const float* Q,
                            const float* K, const float* V, int64_t ld, const float* O,
                            const float* dO, int64_t ldo, const float* lse, float* delta,

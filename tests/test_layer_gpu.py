@@ -304,3 +304,105 @@ def test_layer_gelu_strict_gradients_full_size(precision, tol):
     tgt["grad_params"], tgt["state_after"] = ref["grad_params"], ref["state_after"]
     errs = compare(res, tgt, tol, f"CUDA {precision} GELU strict")
     print("gelu strict", precision, "max err", max(errs.values()))
+
+
+# ------------------------------------------------------------------------------- dropout
+def test_dropout_mask_keep_rate_and_determinism():
+    lib = _lib.load()
+    m1 = torch.empty(512, 304, device=DEV)
+    m2 = torch.empty(512, 304, device=DEV)
+    for p in (0.1, 0.5):
+        _lib.check(lib.gps_dropout_mask(m1.data_ptr(), 512, 304, p, 1234, 4096, 5, _stream()), "mask")
+        _lib.check(lib.gps_dropout_mask(m2.data_ptr(), 512, 304, p, 1234, 4096, 5, _stream()), "mask")
+        assert torch.equal(m1, m2)
+        assert abs(float(m1.mean()) - (1 - p)) < 0.01
+        _lib.check(lib.gps_dropout_mask(m2.data_ptr(), 512, 304, p, 1234, 8192, 5, _stream()), "mask")
+        assert not torch.equal(m1, m2)
+
+
+def _set_dropout_counter(value):
+    from graphgps_b200 import gps_layer
+    dev = torch.device(DEV)
+    ctr = gps_layer._drop_counters.get(dev)
+    if ctr is None:
+        ctr = torch.zeros(1, dtype=torch.int64, device=dev)
+        gps_layer._drop_counters[dev] = ctr
+    ctr.fill_(value)
+
+
+def test_dropout_forward_backward_consistent():
+    """With the Philox offset pinned, the dropout layer is a deterministic smooth (GELU) function: its
+    backward must equal a central finite difference of its forward along a random direction, i.e. the
+    forward and backward passes regenerate the same masks at every dropout site (GatedGCN, attention
+    probabilities, attention output, both FFN sites)."""
+    torch.manual_seed(5)
+    d = 64
+    layer = graphgps_b200.GPSLayer(d, "CustomGatedGCN", "Transformer", 4, act="gelu", dropout=0.2,
+                                   attn_dropout=0.3).to(DEV).train()
+    b = make_batch("zinc-gatedgcn", seed=3, dim=d, num_graphs=12).to(DEV)
+    g = torch.Generator().manual_seed(2)
+    ct_x = torch.randn(b.x.shape, generator=g).to(DEV)
+    ct_e = torch.randn(b.edge_attr.shape, generator=g).to(DEV)
+    vx = torch.randn(b.x.shape, generator=g).to(DEV)
+
+    def f(x):
+        _set_dropout_counter(7 * 4096)
+        bb = graphgps_b200.GraphBatch(x=x, edge_index=b.edge_index, edge_attr=b.edge_attr.clone(), batch=b.batch,
+                                      num_graphs=b.num_graphs)
+        out = layer(bb)
+        return (out.x * ct_x).sum() + (out.edge_attr * ct_e).sum(), out
+
+    x0 = b.x.clone().requires_grad_(True)
+    loss, out0 = f(x0)
+    loss.backward()
+    analytic = float((x0.grad * vx).sum())
+    eps = 1e-2
+    with torch.no_grad():
+        lp, outp = f(b.x + eps * vx)
+        lm, _ = f(b.x - eps * vx)
+        _, out_again = f(b.x.clone())
+    numeric = float((lp - lm) / (2 * eps))
+    assert torch.equal(out_again.x, out0.x.detach())          # pinned offset => identical masks
+    assert abs(numeric - analytic) <= 3e-2 * max(1.0, abs(analytic)), (numeric, analytic)
+    # different offsets => different masks; eval mode => no dropout
+    with torch.no_grad():
+        _set_dropout_counter(9 * 4096)
+        other = layer(graphgps_b200.GraphBatch(x=b.x.clone(), edge_index=b.edge_index, edge_attr=b.edge_attr.clone(),
+                                               batch=b.batch, num_graphs=b.num_graphs))
+    assert not torch.equal(other.x, out0.x.detach())
+
+
+def test_cuda_graph_replay_matches_eager_and_redraws_dropout():
+    torch.manual_seed(1)
+    d = 64
+    layer = graphgps_b200.GPSLayer(d, "CustomGatedGCN", "Transformer", 4, dropout=0.0, attn_dropout=0.0).to(DEV).train()
+    b = make_batch("zinc-gatedgcn", seed=4, dim=d, num_graphs=10).to(DEV)
+    x = b.x.clone().requires_grad_(True)
+    ct = torch.randn_like(b.x)
+
+    def body():
+        bb = graphgps_b200.GraphBatch(x=x, edge_index=b.edge_index, edge_attr=b.edge_attr, batch=b.batch,
+                                      num_graphs=b.num_graphs)
+        if "_gps_b200_graph" in b.__dict__:
+            bb.__dict__["_gps_b200_graph"] = b.__dict__["_gps_b200_graph"]
+        x.grad = None
+        out = layer(bb)
+        torch.autograd.backward([out.x], [ct])
+        return out.x
+
+    graph_of(b)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            body()
+    torch.cuda.current_stream().wait_stream(side)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        y = body()
+    gx_static = x.grad
+    g.replay()
+    torch.cuda.synchronize()
+    y1, gx1 = y.clone(), gx_static.clone()
+    y_eager = body().detach()
+    assert rel_err(y1.cpu(), y_eager.cpu()) < 1e-6 and rel_err(gx1.cpu(), x.grad.cpu()) < 1e-6
