@@ -18,6 +18,22 @@
 
 namespace gps {
 
+// performer.cu
+int perf_supported(int64_t dim_head, int64_t features);
+int64_t perf_mp();
+int perf_prep(const float* P, int64_t m, float* Pn, const GpsGraph& g, int64_t H, int* nmax, float* gmax, int* argk,
+              cudaStream_t st);
+int perf_features_fwd(float* fq, float* fk, const float* Q, const float* K, const GpsGraph& g, int64_t H, int64_t m,
+                      float* gmax, int* argq, int* argk, cudaStream_t st);
+int perf_linattn_fwd(const GpsGraph& g, int64_t H, int64_t m, const int* nmax, const float* qf, const float* kf,
+                     const float* V, const float* gmax, float* O, cudaStream_t st);
+int perf_linattn_bwd(const GpsGraph& g, int64_t H, int64_t m, const int* nmax, const float* qf, const float* kf,
+                     const float* V, const float* gmax, const float* gO, float* g_qf, float* g_kf, float* gV,
+                     float* ggmax, cudaStream_t st);
+int perf_features_bwd(float* g_fq, float* g_fk, const float* fq, const float* fk, const float* Q, const float* K,
+                      float* gQ, float* gK, const GpsGraph& g, int64_t H, int64_t m, const int* argq, const int* argk,
+                      float* ggmax, cudaStream_t st);
+
 // ------------------------------------------------------------------------------- error plumbing
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
@@ -83,7 +99,11 @@ enum { BN_X = 0, BN_E = 1, BN_L = 2, BN_A = 3, BN_2 = 4, BN_COUNT = 5 };
 
 struct Plan {
   int64_t N, E, d, H, hd, Wy, qkv_off;
-  bool gated, gine, attn;
+  bool gated, gine, attn, perf;
+  int64_t inner, mp, m;   // Performer: H*64, padded / real feature count
+  float *pQ, *pK, *pV, *pfq, *pfk, *pPn, *pgmax;   // saved (Performer)
+  int *pargq, *pargk, *pnmax;
+  float *g_pfq, *g_pfk, *g_pQ, *g_pK, *g_pV, *g_pgmax, *g_xp;   // backward workspace (Performer)
   // saved
   float *Wcat, *bcat, *Y1, *ehat, *xt, *xloc, *O, *lse, *hA, *s, *hid, *hid_pre, *t, *bnbuf;
   float *agg, *h1, *h1_pre;
@@ -115,10 +135,16 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
   GPS_REQUIRE(a->global_type == GPS_GLOBAL_NONE || a->global_type == GPS_GLOBAL_TRANSFORMER ||
                   a->global_type == GPS_GLOBAL_PERFORMER,
               GPS_ERR_ARG, "unknown global_type %d", a->global_type);
-  GPS_REQUIRE(a->global_type != GPS_GLOBAL_PERFORMER, GPS_ERR_UNSUPPORTED,
-              "Performer global attention is not built yet in this library version");
   P->attn = a->global_type == GPS_GLOBAL_TRANSFORMER;
-  GPS_REQUIRE(a->local_type != GPS_LOCAL_NONE || P->attn, GPS_ERR_ARG,
+  P->perf = a->global_type == GPS_GLOBAL_PERFORMER;
+  if (P->perf) {
+    GPS_TRY(perf_supported(a->perf_dim_head, a->perf_features));
+    GPS_REQUIRE(a->heads > 0, GPS_ERR_ARG, "num_heads must be positive");
+    P->inner = a->heads * a->perf_dim_head;
+    P->mp = perf_mp();
+    P->m = a->perf_features;
+  }
+  GPS_REQUIRE(a->local_type != GPS_LOCAL_NONE || P->attn || P->perf, GPS_ERR_ARG,
               "GPSLayer needs a local model or a global model");
   if (P->attn) {
     GPS_REQUIRE(a->heads > 0 && a->d % a->heads == 0, GPS_ERR_ARG, "dim_h %% num_heads != 0");
@@ -155,6 +181,21 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
     P->lse = S.alloc<float>(N * P->H);
     P->hA = S.alloc<float>(N * d);
   }
+  if (P->perf) {
+    const int64_t NH = N * P->H, BH = a->graph.B * P->H;
+    P->pQ = S.alloc<float>(N * P->inner);
+    P->pK = S.alloc<float>(N * P->inner);
+    P->pV = S.alloc<float>(N * P->inner);
+    P->pfq = S.alloc<float>(NH * P->mp);
+    P->pfk = S.alloc<float>(NH * P->mp);
+    P->pPn = S.alloc<float>(P->mp * a->perf_dim_head);
+    P->pgmax = S.alloc<float>(BH);
+    P->pargq = S.alloc<int>(NH);
+    P->pargk = S.alloc<int>(BH);
+    P->pnmax = S.alloc<int>(1);
+    P->O = S.alloc<float>(N * P->inner);
+    P->hA = S.alloc<float>(N * d);
+  }
   P->s = S.alloc<float>(N * d);
   P->hid = S.alloc<float>(N * 2 * d);
   if (gelu) P->hid_pre = S.alloc<float>(N * 2 * d);
@@ -179,6 +220,18 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
     P->g_hA = Bk.alloc<float>(N * d);
     P->g_O = Bk.alloc<float>(N * d);
     P->delta = Bk.alloc<float>(N * P->H);
+  }
+  if (P->perf) {
+    const int64_t NH = N * P->H, BH = a->graph.B * P->H;
+    P->g_hA = Bk.alloc<float>(N * d);
+    P->g_O = Bk.alloc<float>(N * P->inner);
+    P->g_pfq = Bk.alloc<float>(NH * P->mp);
+    P->g_pfk = Bk.alloc<float>(NH * P->mp);
+    P->g_pQ = Bk.alloc<float>(N * P->inner);
+    P->g_pK = Bk.alloc<float>(N * P->inner);
+    P->g_pV = Bk.alloc<float>(N * P->inner);
+    P->g_pgmax = Bk.alloc<float>(BH);
+    P->g_xp = Bk.alloc<float>(N * d);
   }
   if (P->Wy) {
     P->gY1 = Bk.alloc<float>(N * P->Wy);
@@ -262,6 +315,14 @@ static int check_params(const GpsLayerArgs* a, const Plan& P) {
   if (P.attn) {
     GPS_TRY(check_linear(a->attn_in, "self_attn.in_proj", true));
     GPS_TRY(check_linear(a->attn_out, "self_attn.out_proj", true));
+    GPS_TRY(check_bn(a->norm1_attn, "norm1_attn"));
+  }
+  if (P.perf) {
+    GPS_TRY(check_linear(a->perf_q, "self_attn.to_q", false));
+    GPS_TRY(check_linear(a->perf_k, "self_attn.to_k", false));
+    GPS_TRY(check_linear(a->perf_v, "self_attn.to_v", false));
+    GPS_TRY(check_linear(a->attn_out, "self_attn.to_out", true));
+    GPS_REQUIRE(a->perf_proj, GPS_ERR_ARG, "missing buffer self_attn.fast_attention.projection_matrix");
     GPS_TRY(check_bn(a->norm1_attn, "norm1_attn"));
   }
   GPS_TRY(check_linear(a->ff1, "ff_linear1", true));
@@ -387,12 +448,46 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(bn_ready(P, a, BN_A, a->norm1_attn, N, st));
   }
 
+  // ---- Performer global attention (gps_layer.py:205-206; performer_layer.py:476-503)
+  if (P.perf) {
+    const int64_t inner = P.inner, NH = N * P.H, dh = a->perf_dim_head;
+    const GpsLinear* lin[3] = {&a->perf_q, &a->perf_k, &a->perf_v};
+    float* dst[3] = {P.pQ, P.pK, P.pV};
+    for (int i = 0; i < 3; ++i) {   // q, k, v = x W^T (no bias)
+      GemmParams g;
+      g.M = (int)N; g.N = (int)inner; g.K = (int)d;
+      g.A = a->x; g.lda = (int)d; g.B = lin[i]->weight; g.ldb = (int)d; g.C = dst[i]; g.ldc = (int)inner;
+      g.precision = a->precision;
+      GPS_TRY(gemm(g, st));
+    }
+    GPS_TRY(perf_prep(a->perf_proj, P.m, P.pPn, a->graph, P.H, P.pnmax, P.pgmax, P.pargk, st));
+    float* ddst[2] = {P.pfq, P.pfk};
+    for (int i = 0; i < 2; ++i) {   // dd = (x dn) P^T for every (node, head) row
+      GemmParams g;
+      g.M = (int)NH; g.N = (int)P.mp; g.K = (int)dh;
+      g.A = dst[i]; g.lda = (int)dh; g.B = P.pPn; g.ldb = (int)dh; g.C = ddst[i]; g.ldc = (int)P.mp;
+      g.precision = a->precision;
+      GPS_TRY(gemm(g, st));
+    }
+    GPS_TRY(perf_features_fwd(P.pfq, P.pfk, P.pQ, P.pK, a->graph, P.H, P.m, P.pgmax, P.pargq, P.pargk, st));
+    GPS_TRY(perf_linattn_fwd(a->graph, P.H, P.m, P.pnmax, P.pfq, P.pfk, P.pV, P.pgmax, P.O, st));
+    GemmParams g;  // hA = x + drop(to_out(O))
+    g.M = (int)N; g.N = (int)d; g.K = (int)inner;
+    g.A = P.O; g.lda = (int)inner; g.B = a->attn_out.weight; g.ldb = (int)inner; g.C = P.hA; g.ldc = (int)d;
+    g.bias = a->attn_out.bias; g.R1 = a->x; g.ldr1 = (int)d; g.stats = stats(BN_A);
+    g.p_drop = pd > 0.f ? pd : 0.f; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_ATTN_OUT;
+    g.offset_dev = (const unsigned long long*)a->offset_dev;
+    g.precision = a->precision;
+    GPS_TRY(gemm(g, st));
+    GPS_TRY(bn_ready(P, a, BN_A, a->norm1_attn, N, st));
+  }
+
   // ---- s = norm1_local(x_loc) + norm1_attn(hA)   (gps_layer.py:194,217,222)
   {
     const bool loc = P.gated || P.gine;
     const float* first = loc ? P.xloc : P.hA;
     BnView bf = loc ? bn_view(P, BN_L, a->norm1_local) : bn_view(P, BN_A, a->norm1_attn);
-    const float* second = (loc && P.attn) ? P.hA : nullptr;
+    const float* second = (loc && (P.attn || P.perf)) ? P.hA : nullptr;
     BnView bs = bn_view(P, BN_A, a->norm1_attn);
     GPS_TRY(bn_combine(first, bf, second, bs, P.s, N, d, st));
   }
@@ -508,6 +603,50 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
                           gQ + 2 * d, P.Wy, pa, a->seed, a->offset, st, (const unsigned long long*)a->offset_dev));
   }
 
+  if (P.perf) {
+    const int64_t inner = P.inner, NH = N * P.H, dh = a->perf_dim_head;
+    BnView v = bn_view(P, BN_A, a->norm1_attn);
+    GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), st));
+    GPS_TRY(bn_bwd_apply(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), P.g_hA, d, a->norm1_attn.grad_weight,
+                         a->norm1_attn.grad_bias, st));
+    const float* g_ao = P.g_hA;   // hA = x + drop(to_out(O))
+    if (pd > 0.f) {
+      GPS_TRY(dropmul(P.g_hA, P.g_tmp, N, d, P, a, GPS_SITE_ATTN_OUT, st));
+      g_ao = P.g_tmp;
+    }
+    GemmParams g;  // g_O = g_ao Wout   [N, inner]
+    g.M = (int)N; g.N = (int)inner; g.K = (int)d;
+    g.A = g_ao; g.lda = (int)d; g.B = a->attn_out.weight; g.ldb = (int)inner; g.tb = 1; g.C = P.g_O; g.ldc = (int)inner;
+    g.precision = prec;
+    GPS_TRY(gemm(g, st));
+    GPS_TRY(linear_wgrad(g_ao, d, P.O, inner, N, d, inner, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, st));
+    // linear attention and feature maps (performer_layer.py:200-205, 119-144)
+    GPS_TRY(perf_linattn_bwd(a->graph, P.H, P.m, P.pnmax, P.pfq, P.pfk, P.pV, P.pgmax, P.g_O, P.g_pfq, P.g_pfk, P.g_pV,
+                             P.g_pgmax, st));
+    GPS_TRY(perf_features_bwd(P.g_pfq, P.g_pfk, P.pfq, P.pfk, P.pQ, P.pK, P.g_pQ, P.g_pK, a->graph, P.H, P.m, P.pargq,
+                              P.pargk, P.g_pgmax, st));
+    float* gdd[2] = {P.g_pfq, P.g_pfk};
+    float* gqk[2] = {P.g_pQ, P.g_pK};
+    for (int i = 0; i < 2; ++i) {   // g_q += g_dd Pn   (dd = q Pn^T)
+      GemmParams h;
+      h.M = (int)NH; h.N = (int)dh; h.K = (int)P.mp;
+      h.A = gdd[i]; h.lda = (int)P.mp; h.B = P.pPn; h.ldb = (int)dh; h.tb = 1; h.C = gqk[i]; h.ldc = (int)dh;
+      h.R1 = gqk[i]; h.ldr1 = (int)dh; h.precision = prec;
+      GPS_TRY(gemm(h, st));
+    }
+    // projections: dW = g^T x ;  g_xp = g_hA + gQ Wq + gK Wk + gV Wv
+    const GpsLinear* lin[3] = {&a->perf_q, &a->perf_k, &a->perf_v};
+    const float* gsrc[3] = {P.g_pQ, P.g_pK, P.g_pV};
+    for (int i = 0; i < 3; ++i) {
+      GPS_TRY(linear_wgrad(gsrc[i], inner, a->x, d, N, inner, d, lin[i]->grad_weight, nullptr, prec, st));
+      GemmParams h;
+      h.M = (int)N; h.N = (int)d; h.K = (int)inner;
+      h.A = gsrc[i]; h.lda = (int)inner; h.B = lin[i]->weight; h.ldb = (int)d; h.tb = 1; h.C = P.g_xp; h.ldc = (int)d;
+      h.R1 = i == 0 ? P.g_hA : P.g_xp; h.ldr1 = (int)d; h.precision = prec;
+      GPS_TRY(gemm(h, st));
+    }
+  }
+
   // ---- local model backward
   const float* g_x_local = nullptr;  // direct gradient paths into x besides the projections
   if (P.gated) {
@@ -582,11 +721,13 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g.M = (int)N; g.N = (int)d; g.K = (int)P.Wy;
     g.A = P.gY1; g.lda = (int)P.Wy; g.B = P.Wcat; g.ldb = (int)d; g.tb = 1; g.C = a->grad_x; g.ldc = (int)d;
     g.R1 = g_x_local; g.ldr1 = (int)d;
-    g.R2 = P.attn ? P.g_hA : nullptr; g.ldr2 = (int)d;
+    g.R2 = P.attn ? P.g_hA : (P.perf ? P.g_xp : nullptr); g.ldr2 = (int)d;
     g.precision = prec;
     GPS_TRY(gemm(g, st));
+  } else if (g_x_local) {
+    GPS_TRY(add3(g_x_local, d, P.perf ? P.g_xp : nullptr, d, nullptr, 0, a->grad_x, d, N, d, st));
   } else {
-    GPS_TRY(add3(g_x_local, d, nullptr, 0, nullptr, 0, a->grad_x, d, N, d, st));
+    GPS_TRY(add3(P.g_xp, d, nullptr, 0, nullptr, 0, a->grad_x, d, N, d, st));   // Performer only
   }
   return GPS_OK;
 }

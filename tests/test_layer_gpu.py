@@ -161,8 +161,6 @@ def _build(cfg, precision="fp32", **kw):
 def test_layer_matches_golden(name, precision):
     fix = load_golden(name)
     cfg = fix["config"]
-    if cfg["glob"] == "Performer":
-        pytest.xfail("Performer global model not built yet")
     layer = _build(cfg, precision)
     layer.load_state_dict(fix["state"], strict=True)
     layer = layer.to(DEV).train(cfg["training"])
@@ -173,7 +171,10 @@ def test_layer_matches_golden(name, precision):
 
 @pytest.mark.parametrize("shape,local,glob,heads", [("pcqm4m-small", "CustomGatedGCN", "Transformer", 4),
                                                     ("zinc-gine", "GINE", "Transformer", 4),
-                                                    ("code2", "CustomGatedGCN", "Transformer", 4)])
+                                                    ("code2", "CustomGatedGCN", "Transformer", 4),
+                                                    ("pcqm4m-medium-performer", "CustomGatedGCN", "Performer", 16),
+                                                    ("zinc-gatedgcn", "None", "Performer", 4),
+                                                    ("code2", "CustomGatedGCN", "Performer", 4)])
 def test_layer_matches_oracle_full_size(shape, local, glob, heads):
     """BASELINE-size batch: CUDA layer vs the oracle on the same seeded inputs and weights.
 
