@@ -43,11 +43,24 @@ __device__ __forceinline__ int warp_max_i(int v) {
   return v;
 }
 
-__device__ __forceinline__ float drop_scale_pair(float p, uint64_t seed, uint64_t offset, int head, int i, int jl) {
-  if (p <= 0.f) return 1.f;
-  Philox4 r = philox4x32(seed, offset + (uint64_t)(GPS_SITE_ATTN_P + head), ((uint64_t)i << 20) | (uint64_t)(jl >> 2));
-  uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
-  return r.v[jl & 3] >= thr ? 1.f / (1.f - p) : 0.f;
+// Dropout on the attention probabilities: one Philox call yields the keep decisions of 4 consecutive keys
+// (query i, keys 4*(jl>>2) .. +3) of one head; callers cache it across those 4 loop iterations.
+struct DropQuad {
+  Philox4 r;
+  uint32_t thr;
+  float keep_scale;
+};
+__device__ __forceinline__ void drop_quad_refresh(DropQuad& q, float p, uint64_t seed, uint64_t offset, int head, int i, int jl) {
+  q.r = philox4x32(seed, offset + (uint64_t)(GPS_SITE_ATTN_P + head), ((uint64_t)i << 20) | (uint64_t)(jl >> 2));
+}
+__device__ __forceinline__ float drop_quad_scale(const DropQuad& q, int jl) {
+  const int k = jl & 3;
+  const uint32_t bits = k == 0 ? q.r.v[0] : k == 1 ? q.r.v[1] : k == 2 ? q.r.v[2] : q.r.v[3];
+  return bits >= q.thr ? q.keep_scale : 0.f;
+}
+__device__ __forceinline__ void drop_quad_init(DropQuad& q, float p) {
+  q.thr = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
+  q.keep_scale = 1.f / (1.f - p);
 }
 
 // lane-slice helpers: lane `sub` of a row group owns float4 chunks sub, sub+LPR, ... (< nch)
@@ -114,7 +127,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_fwd(AttnArgs a) {
     o[c] = f4zero();
   }
   float m = -INFINITY, l = 0.f;
+  const bool use_drop = a.p_drop > 0.f;
+  DropQuad dq;
+  drop_quad_init(dq, a.p_drop);
   for (int jl = 0; jl < nloop; ++jl) {
+    if (use_drop && (jl & 3) == 0) drop_quad_refresh(dq, a.p_drop, a.seed, offs, h, i, jl);
     const bool valid = jl < n;
     const int j = gs + (valid ? jl : 0);
     float4 kv[CH];
@@ -125,7 +142,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_fwd(AttnArgs a) {
     const float corr = (m_new == -INFINITY) ? 1.f : __expf(m - m_new);
     const float p = valid ? __expf(s - m_new) : 0.f;
     l = l * corr + p;
-    const float pd = p * drop_scale_pair(a.p_drop, a.seed, offs, h, i, jl);
+    const float pd = use_drop ? p * drop_quad_scale(dq, jl) : p;
     load_slice<CH, LPR>(kv, a.V + (int64_t)j * a.ld + hoff, sub, nch, valid);
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
@@ -179,7 +196,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_q(AttnArgs a) 
     const float lse = row_ok ? a.lsec[(int64_t)i * a.H + h] : 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) q[c] = f4scale(q[c], a.scale);
+    const bool use_drop = a.p_drop > 0.f;
+    DropQuad dq;
+    drop_quad_init(dq, a.p_drop);
     for (int jl = 0; jl < nloop; ++jl) {
+      if (use_drop && (jl & 3) == 0) drop_quad_refresh(dq, a.p_drop, a.seed, offs, h, i, jl);
       const bool valid = jl < n;
       const int j = gs + (valid ? jl : 0);
       float4 kk[CH], vv[CH];
@@ -192,7 +213,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_q(AttnArgs a) 
         dp += __shfl_xor_sync(0xffffffffu, dp, ofs);
       }
       const float p = valid ? __expf(s - lse) : 0.f;
-      const float ds = p * (dp * drop_scale_pair(a.p_drop, a.seed, offs, h, i, jl) - dl);
+      const float ds = p * (dp * (use_drop ? drop_quad_scale(dq, jl) : 1.f) - dl);
 #pragma unroll
       for (int c = 0; c < CH; ++c) {
         gq[c].x += ds * kk[c].x;
@@ -253,7 +274,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_kv(AttnArgs a)
     const float lse = valid ? a.lsec[(int64_t)i * a.H + h] : 0.f;
     const float dl = valid ? a.deltac[(int64_t)i * a.H + h] : 0.f;
     const float p = valid ? __expf(s * a.scale - lse) : 0.f;
-    const float dsc = drop_scale_pair(a.p_drop, a.seed, offs, h, i, jl);
+    float dsc = 1.f;
+    if (a.p_drop > 0.f) {
+      DropQuad dq;
+      drop_quad_init(dq, a.p_drop);
+      drop_quad_refresh(dq, a.p_drop, a.seed, offs, h, i, jl);
+      dsc = drop_quad_scale(dq, jl);
+    }
     const float pd = p * dsc;
     const float ds = p * (dp * dsc - dl) * a.scale;
 #pragma unroll

@@ -19,9 +19,20 @@ static int row_geom(int64_t rows, int64_t d, int nstat, RowGeom* g) {
   GPS_REQUIRE(d > 0 && d % 4 == 0 && d / 4 <= 1024, GPS_ERR_UNSUPPORTED,
               "row-wise stage needs d %% 4 == 0 and d <= 4096 (got %lld)", (long long)d);
   int C4 = (int)(d / 4);
+  // Kernels that end with column statistics add 2*NS*d doubles per CTA onto the same d addresses, and
+  // same-address L2 atomics serialise (~50 ns each: 300 CTAs cost ~17 us for a 4.4 MB reduce whose loads
+  // need ~3 us).  So: few, fat CTAs (up to 1024 threads) when there are statistics, many small ones otherwise.
   int RY = C4 >= 256 ? 1 : 256 / C4;
+  int64_t cap = kNumSMs * 8;
+  if (nstat > 0) {
+    RY = C4 >= 1024 ? 1 : 1024 / C4;
+    if (RY > 16) RY = 16;
+    const int smem_cap = (int)(48 * 1024 / ((size_t)nstat * C4 * sizeof(float4)));   // static 48 KB limit
+    if (RY > smem_cap) RY = smem_cap < 1 ? 1 : smem_cap;
+    cap = kNumSMs / 2;
+  }
   int64_t blocks = ceil_div(rows > 0 ? rows : 1, (int64_t)RY * 4);
-  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  if (blocks > cap) blocks = cap;
   g->block = dim3(C4, RY, 1);
   g->grid = dim3((unsigned)blocks, 1, 1);
   g->smem = RY > 1 ? (size_t)nstat * RY * C4 * sizeof(float4) : 0;
@@ -29,7 +40,7 @@ static int row_geom(int64_t rows, int64_t d, int nstat, RowGeom* g) {
 }
 
 template <class Op>
-__global__ void k_rowwise(Op op, int64_t rows) {
+__global__ void __launch_bounds__(1024) k_rowwise(Op op, int64_t rows) {
   extern __shared__ float4 sm[];
   const int c4 = threadIdx.x, ry = threadIdx.y, RY = blockDim.y, C4 = blockDim.x;
   constexpr int NS = Op::NS;
@@ -37,6 +48,7 @@ __global__ void k_rowwise(Op op, int64_t rows) {
 #pragma unroll
   for (int s = 0; s < (NS > 0 ? NS : 1); ++s) acc[s] = f4zero();
   op.prepare(c4);
+#pragma unroll 4
   for (int64_t r = (int64_t)blockIdx.x * RY + ry; r < rows; r += (int64_t)gridDim.x * RY) op.row(r, c4, acc);
   if (NS > 0) {
     if (RY > 1) {

@@ -184,8 +184,11 @@ struct TcArgs {
   int debug;       // perf-triage switches (gps_debug_set): 1 no global loads, 2 no convert/store, 4 no MMA, 8 no epilogue
 };
 
-template <bool A_MN, bool B_MN, bool SPLIT>
-__global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
+// NBC = B chunks per producer thread per k-block (2: tiles up to 64 columns, 8: up to 256).  The narrow variant
+// fits in 112 registers and ~100 KB of shared memory, so two CTAs share an SM and one CTA's load/convert phase
+// overlaps the other's MMA/epilogue phase.
+template <bool A_MN, bool B_MN, bool SPLIT, int NBC>
+__global__ void __launch_bounds__(kThreads, NBC == 2 ? 2 : 1) k_gemm_tc(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const GemmParams& p = a.p;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
       const int s = i % S;
       const uint32_t ph = (uint32_t)(i / S) & 1u;
       const int krem = k_end - (kb_begin + i) * BK;     // valid k extent of this k-block (<= 64 on the tail)
-      float4 va[4][2], vb[8][2];
+      float4 va[4][2], vb[NBC][2];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const bool ok = !(a.debug & 1) && (A_MN ? (a_row0 < p.M && a_k0 + q * (kProducerThreads >> a_rcs) < krem)
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
         va[q][1] = ok ? ld4(src + 4) : f4zero();
       }
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < NBC; ++q) {
         const bool ok = !(a.debug & 1) && q < nb_chunks &&
                         (B_MN ? (b_row0 < p.N && b_k0 + q * (kProducerThreads >> b_rcs) < krem)
                               : (b_row0 + 32 * q < p.N && b_k0 < krem));
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
           if (SPLIT) *reinterpret_cast<uint4*>(sa_lo + a_s0 + q * a_sq) = lo;
         }
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
+        for (int q = 0; q < NBC; ++q)
           if (q < nb_chunks) {
             uint4 hi, lo;
             split8(reinterpret_cast<const float*>(vb[q]), hi, lo);
@@ -384,8 +387,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_gemm_tc(const TcArgs a) {
           if (row_ok) {
             float* dst = p.C + (int64_t)row * p.ldc + gn;
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-              if (gn + e < p.N) atomicAdd(dst + e, v[e]);
+            for (int e = 0; e < 16; e += 4)   // N % 4 == 0: whole 16-byte groups; red.global.add.v4.f32
+              if (gn + e < p.N) atomicAdd(reinterpret_cast<float4*>(dst + e), make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
           }
           continue;
         }
@@ -482,16 +485,21 @@ int g_tc_debug = 0;
 
 inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
-template <bool A_MN, bool B_MN, bool SPLIT>
-int launch(const TcArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
+template <bool A_MN, bool B_MN, bool SPLIT, int NBC>
+int launch1(const TcArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    GPS_CUDA(cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GPS_CUDA(cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN, SPLIT, NBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_done = true;
   }
-  k_gemm_tc<A_MN, B_MN, SPLIT><<<grid, kThreads, smem, stream>>>(a);
+  k_gemm_tc<A_MN, B_MN, SPLIT, NBC><<<grid, kThreads, smem, stream>>>(a);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
+}
+template <bool A_MN, bool B_MN, bool SPLIT>
+int launch(const TcArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
+  return a.nb_blocks == 1 ? launch1<A_MN, B_MN, SPLIT, 2>(a, grid, smem, stream)
+                          : launch1<A_MN, B_MN, SPLIT, 8>(a, grid, smem, stream);
 }
 
 }  // namespace
@@ -542,7 +550,7 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
     if (bn < 16) bn = 16;
     int nb = bn <= 64 ? 1 : bn <= 128 ? 2 : 4;
     long tiles = (long)mt * ceil_div(p.N, bn) * splits_hint;
-    long waves = ceil_div(tiles, kNumSMs);
+    long waves = ceil_div(tiles, nb == 1 ? 2L * kNumSMs : (long)kNumSMs);   // narrow tiles: two CTAs per SM
     long cost = waves * (BM + nb * 64L);
     if (bestCost < 0 || cost < bestCost) { bestCost = cost; bestBN = bn; }
   }
@@ -551,7 +559,7 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
   a.BN = bestBN;
   a.nb_blocks = a.BN <= 64 ? 1 : a.BN <= 128 ? 2 : 4;
   const int stage_bytes = plane * (kATileBytes + a.nb_blocks * kBBlockBytes);
-  int stages = (200 * 1024) / stage_bytes;
+  int stages = ((a.nb_blocks == 1 ? 100 : 200) * 1024) / stage_bytes;   // narrow tiles leave room for a second CTA
   if (stages > 4) stages = 4;
   if (stages < 2) return GPS_ERR_UNSUPPORTED;
   a.stages = stages;

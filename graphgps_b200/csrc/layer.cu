@@ -64,6 +64,50 @@ int gemm(const GemmParams& p, cudaStream_t stream) {
 
 namespace {
 
+// ------------------------------------------------------------------------------- side stream (fork / join)
+// Independent stages run concurrently with the main chain: the edge projection next to the node projections, the
+// attention branch next to the message-passing branch (gps_layer.py:161-218 computes both from the same h_in1),
+// and every weight-gradient GEMM next to the data-gradient chain.  Fork = event on the caller's stream that the
+// side stream waits on; join = the reverse.  All of it is capturable into a CUDA graph.
+struct Side {
+  cudaStream_t s = nullptr;
+  cudaEvent_t ev[32];
+  int next = 0;
+  bool ok = false;
+  int init() {
+    if (ok) return GPS_OK;
+    GPS_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (int i = 0; i < 32; ++i) GPS_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    ok = true;
+    return GPS_OK;
+  }
+  int fork(cudaStream_t main) {   // side waits for everything enqueued on main so far
+    cudaEvent_t e = ev[next++ & 31];
+    GPS_CUDA(cudaEventRecord(e, main));
+    GPS_CUDA(cudaStreamWaitEvent(s, e, 0));
+    return GPS_OK;
+  }
+  int join(cudaStream_t main) {   // main waits for everything enqueued on side so far
+    cudaEvent_t e = ev[next++ & 31];
+    GPS_CUDA(cudaEventRecord(e, s));
+    GPS_CUDA(cudaStreamWaitEvent(main, e, 0));
+    return GPS_OK;
+  }
+};
+
+static Side* side_stream() {
+  static const bool enabled = [] {
+    const char* e = getenv("GPS_B200_STREAMS");
+    return !(e && e[0] == '0');
+  }();
+  if (!enabled) return nullptr;
+  static thread_local Side sides[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (sides[dev].init() != GPS_OK) return nullptr;
+  return &sides[dev];
+}
+
 // ------------------------------------------------------------------------------- weight packing
 struct PackSeg {
   const float* w; const float* b; float* gw; float* gb; int rows;
@@ -73,26 +117,26 @@ struct PackDesc {
   int nseg; int d; int total_rows;
 };
 
-// cat[r, :] = seg.w[r - row0, :], bcat[r] = seg.b[...] (0 when the Linear has no bias)
+// cat[r, :] = seg.w[r - row0, :], bcat[r] = seg.b[...] (0 when the Linear has no bias).  One row per blockIdx.x.
 __global__ void k_pack(PackDesc pd, float* __restrict__ Wcat, float* __restrict__ bcat) {
-  const int64_t total = (int64_t)pd.total_rows * pd.d;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int r = (int)(i / pd.d), c = (int)(i % pd.d);
-    int row0 = 0, s = 0;
-    while (s < pd.nseg - 1 && r >= row0 + pd.seg[s].rows) row0 += pd.seg[s++].rows;
-    Wcat[i] = pd.seg[s].w[(int64_t)(r - row0) * pd.d + c];
-    if (c == 0) bcat[r] = pd.seg[s].b ? pd.seg[s].b[r - row0] : 0.f;
-  }
+  const int r = blockIdx.x;
+  int row0 = 0, s = 0;
+  while (s < pd.nseg - 1 && r >= row0 + pd.seg[s].rows) row0 += pd.seg[s++].rows;
+  const float* src = pd.seg[s].w + (int64_t)(r - row0) * pd.d;
+  float* dst = Wcat + (int64_t)r * pd.d;
+  for (int c = threadIdx.x * 4; c < pd.d; c += blockDim.x * 4) st4(dst + c, ld4(src + c));
+  if (threadIdx.x == 0) bcat[r] = pd.seg[s].b ? pd.seg[s].b[r - row0] : 0.f;
 }
 __global__ void k_unpack(PackDesc pd, const float* __restrict__ gWcat, const float* __restrict__ gbcat) {
-  const int64_t total = (int64_t)pd.total_rows * pd.d;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int r = (int)(i / pd.d), c = (int)(i % pd.d);
-    int row0 = 0, s = 0;
-    while (s < pd.nseg - 1 && r >= row0 + pd.seg[s].rows) row0 += pd.seg[s++].rows;
-    if (pd.seg[s].gw) pd.seg[s].gw[(int64_t)(r - row0) * pd.d + c] = gWcat[i];
-    if (c == 0 && pd.seg[s].gb) pd.seg[s].gb[r - row0] = gbcat[r];
+  const int r = blockIdx.x;
+  int row0 = 0, s = 0;
+  while (s < pd.nseg - 1 && r >= row0 + pd.seg[s].rows) row0 += pd.seg[s++].rows;
+  if (pd.seg[s].gw) {
+    float* dst = pd.seg[s].gw + (int64_t)(r - row0) * pd.d;
+    const float* src = gWcat + (int64_t)r * pd.d;
+    for (int c = threadIdx.x * 4; c < pd.d; c += blockDim.x * 4) st4(dst + c, ld4(src + c));
   }
+  if (threadIdx.x == 0 && pd.seg[s].gb) pd.seg[s].gb[r - row0] = gbcat[r];
 }
 
 enum { BN_X = 0, BN_E = 1, BN_L = 2, BN_A = 3, BN_2 = 4, BN_COUNT = 5 };
@@ -113,7 +157,7 @@ struct Plan {
   int64_t fwd_bytes;
   // backward workspace
   double* bsums;
-  float *g_t, *g_hid, *g_s, *g_xloc, *g_hA, *g_O, *gY1, *g_e, *g_num, *delta, *g_tmp, *g_h1, *g_agg, *gWcat,
+  float *g_t, *g_hid, *g_s, *g_xloc, *g_hA, *g_O, *gY1, *g_e, *g_num, *delta, *g_tmp, *g_tmp2, *g_tmp3, *g_h1, *g_agg, *gWcat,
       *gbcat, *g_xl;
   int64_t bwd_bytes;
   int64_t fwd_launches, bwd_launches;
@@ -215,6 +259,10 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
   P->g_hid = Bk.alloc<float>(N * 2 * d);
   P->g_s = Bk.alloc<float>(N * d);
   P->g_tmp = Bk.alloc<float>(N * d);
+  if (a->dropout > 0.f) {   // separate dropout temporaries: side-stream weight gradients still read the earlier ones
+    P->g_tmp2 = Bk.alloc<float>(N * d);
+    P->g_tmp3 = Bk.alloc<float>(N * d);
+  }
   if (P->gated || P->gine) P->g_xloc = Bk.alloc<float>(N * d);
   if (P->attn) {
     P->g_hA = Bk.alloc<float>(N * d);
@@ -235,8 +283,8 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
   }
   if (P->Wy) {
     P->gY1 = Bk.alloc<float>(N * P->Wy);
-    P->gWcat = Bk.alloc<float>(P->Wy * d);
-    P->gbcat = Bk.alloc<float>(P->Wy);
+    P->gWcat = Bk.alloc<float>(P->Wy * d + P->Wy);   // [gWcat | gbcat] contiguous: one memset
+    P->gbcat = P->gWcat ? P->gWcat + P->Wy * d : nullptr;
   }
   if (P->gated) {
     P->g_e = Bk.alloc<float>(E * d);
@@ -331,6 +379,10 @@ static int check_params(const GpsLayerArgs* a, const Plan& P) {
   return GPS_OK;
 }
 
+// set per call from GpsLayerArgs.reserved0 bit 0: the caller already zeroed every parameter-gradient buffer
+// (one multi-tensor fill instead of a memset per weight and bias)
+static thread_local bool g_grads_prezeroed = false;
+
 static int splitk_for(int64_t rows) {
   // reduction over `rows` (nodes/edges) for weight gradients: enough CTAs to fill the machine
   int64_t s = rows / 256;
@@ -343,8 +395,10 @@ static int splitk_for(int64_t rows) {
 static int linear_wgrad(const float* G, int64_t ldg, const float* X, int64_t ldx, int64_t rows, int64_t out,
                         int64_t in, float* dW, float* db, int precision, cudaStream_t st) {
   if (!dW) return GPS_OK;
-  GPS_CUDA(cudaMemsetAsync(dW, 0, (size_t)(out * in) * sizeof(float), st));
-  if (db) GPS_CUDA(cudaMemsetAsync(db, 0, (size_t)out * sizeof(float), st));
+  if (!g_grads_prezeroed) {
+    GPS_CUDA(cudaMemsetAsync(dW, 0, (size_t)(out * in) * sizeof(float), st));
+    if (db) GPS_CUDA(cudaMemsetAsync(db, 0, (size_t)out * sizeof(float), st));
+  }
   if (rows == 0) return GPS_OK;
   GemmParams p;
   p.M = (int)out; p.N = (int)in; p.K = (int)rows;
@@ -383,11 +437,24 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
   auto stats = [&](int which) -> double* { return train ? P.fstats + (int64_t)which * 2 * d : nullptr; };
 
   if (train) GPS_CUDA(cudaMemsetAsync(P.fstats, 0, (size_t)BN_COUNT * 2 * d * sizeof(double), st));
+  Side* sd = side_stream();
+  cudaStream_t s2 = sd ? sd->s : st;
+  const bool two_branches = (P.gated || P.gine) && (P.attn || P.perf);
+
+  if (P.gated) {   // edge projection has no dependency on the node side: run it next to the node projections
+    GPS_REQUIRE(a->edge_out, GPS_ERR_ARG, "edge_out is null");
+    if (sd) GPS_TRY(sd->fork(st));
+    GemmParams g;  // Ce = e C^T + bC (gatedgcn_layer.py:59)
+    g.M = (int)E; g.N = (int)d; g.K = (int)d;
+    g.A = a->edge_attr; g.lda = (int)d; g.B = a->gcn_C.weight; g.ldb = (int)d; g.C = P.ehat; g.ldc = (int)d;
+    g.bias = a->gcn_C.bias; g.precision = a->precision;
+    GPS_TRY(gemm(g, s2));
+  }
 
   // ---- node projections: [Ax|Bx|Dx|Ex|Q|K|V] = x Wcat^T + bcat  (gatedgcn_layer.py:57-61, MHA in_proj)
   if (P.Wy) {
     PackDesc pdsc = pack_desc(a, P);
-    k_pack<<<kNumSMs * 2, 256, 0, st>>>(pdsc, P.Wcat, P.bcat);
+    k_pack<<<(unsigned)pdsc.total_rows, 128, 0, st>>>(pdsc, P.Wcat, P.bcat);
     GPS_LAUNCH_CHECK();
     GemmParams g;
     g.M = (int)N; g.N = (int)P.Wy; g.K = (int)d;
@@ -396,14 +463,16 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(gemm(g, st));
   }
 
+  // main waits for the edge projection; then the global branch forks off the node projections
+  if (P.gated && sd) GPS_TRY(sd->join(st));
+  cudaStream_t sg = st;   // stream of the global-attention branch
+  if (two_branches && sd) {
+    GPS_TRY(sd->fork(st));
+    sg = s2;
+  }
+
   // ---- local model
   if (P.gated) {
-    GPS_REQUIRE(a->edge_out, GPS_ERR_ARG, "edge_out is null");
-    GemmParams g;  // Ce = e C^T + bC (gatedgcn_layer.py:59)
-    g.M = (int)E; g.N = (int)d; g.K = (int)d;
-    g.A = a->edge_attr; g.lda = (int)d; g.B = a->gcn_C.weight; g.ldb = (int)d; g.C = P.ehat; g.ldc = (int)d;
-    g.bias = a->gcn_C.bias; g.precision = a->precision;
-    GPS_TRY(gemm(g, st));
     GPS_TRY(gatedgcn_fwd(a->graph, d, P.Y1, P.Y1 + d, P.Y1 + 2 * d, P.Y1 + 3 * d, P.Wy, P.ehat, P.xt,
                          stats(BN_X), stats(BN_E), st));
     GPS_TRY(bn_ready(P, a, BN_X, a->bn_node_x, N, st));
@@ -435,7 +504,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
   // ---- global attention  (gps_layer.py:198-218, 234-241)
   if (P.attn) {
     const float* Q = P.Y1 + P.qkv_off;
-    GPS_TRY(attention_fwd(a->graph, P.H, P.hd, Q, Q + d, Q + 2 * d, P.Wy, P.O, d, P.lse, pa, a->seed, a->offset, st,
+    GPS_TRY(attention_fwd(a->graph, P.H, P.hd, Q, Q + d, Q + 2 * d, P.Wy, P.O, d, P.lse, pa, a->seed, a->offset, sg,
                           (const unsigned long long*)a->offset_dev));
     GemmParams g;  // hA = x + drop(O Wo^T + bo)
     g.M = (int)N; g.N = (int)d; g.K = (int)d;
@@ -444,8 +513,8 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.p_drop = pd; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_ATTN_OUT;
     g.offset_dev = (const unsigned long long*)a->offset_dev;
     g.precision = a->precision;
-    GPS_TRY(gemm(g, st));
-    GPS_TRY(bn_ready(P, a, BN_A, a->norm1_attn, N, st));
+    GPS_TRY(gemm(g, sg));
+    GPS_TRY(bn_ready(P, a, BN_A, a->norm1_attn, N, sg));
   }
 
   // ---- Performer global attention (gps_layer.py:205-206; performer_layer.py:476-503)
@@ -458,19 +527,19 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
       g.M = (int)N; g.N = (int)inner; g.K = (int)d;
       g.A = a->x; g.lda = (int)d; g.B = lin[i]->weight; g.ldb = (int)d; g.C = dst[i]; g.ldc = (int)inner;
       g.precision = a->precision;
-      GPS_TRY(gemm(g, st));
+      GPS_TRY(gemm(g, sg));
     }
-    GPS_TRY(perf_prep(a->perf_proj, P.m, P.pPn, a->graph, P.H, P.pnmax, P.pgmax, P.pargk, st));
+    GPS_TRY(perf_prep(a->perf_proj, P.m, P.pPn, a->graph, P.H, P.pnmax, P.pgmax, P.pargk, sg));
     float* ddst[2] = {P.pfq, P.pfk};
     for (int i = 0; i < 2; ++i) {   // dd = (x dn) P^T for every (node, head) row
       GemmParams g;
       g.M = (int)NH; g.N = (int)P.mp; g.K = (int)dh;
       g.A = dst[i]; g.lda = (int)dh; g.B = P.pPn; g.ldb = (int)dh; g.C = ddst[i]; g.ldc = (int)P.mp;
       g.precision = a->precision;
-      GPS_TRY(gemm(g, st));
+      GPS_TRY(gemm(g, sg));
     }
-    GPS_TRY(perf_features_fwd(P.pfq, P.pfk, P.pQ, P.pK, a->graph, P.H, P.m, P.pgmax, P.pargq, P.pargk, st));
-    GPS_TRY(perf_linattn_fwd(a->graph, P.H, P.m, P.pnmax, P.pfq, P.pfk, P.pV, P.pgmax, P.O, st));
+    GPS_TRY(perf_features_fwd(P.pfq, P.pfk, P.pQ, P.pK, a->graph, P.H, P.m, P.pgmax, P.pargq, P.pargk, sg));
+    GPS_TRY(perf_linattn_fwd(a->graph, P.H, P.m, P.pnmax, P.pfq, P.pfk, P.pV, P.pgmax, P.O, sg));
     GemmParams g;  // hA = x + drop(to_out(O))
     g.M = (int)N; g.N = (int)d; g.K = (int)inner;
     g.A = P.O; g.lda = (int)inner; g.B = a->attn_out.weight; g.ldb = (int)inner; g.C = P.hA; g.ldc = (int)d;
@@ -478,9 +547,11 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.p_drop = pd > 0.f ? pd : 0.f; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_ATTN_OUT;
     g.offset_dev = (const unsigned long long*)a->offset_dev;
     g.precision = a->precision;
-    GPS_TRY(gemm(g, st));
-    GPS_TRY(bn_ready(P, a, BN_A, a->norm1_attn, N, st));
+    GPS_TRY(gemm(g, sg));
+    GPS_TRY(bn_ready(P, a, BN_A, a->norm1_attn, N, sg));
   }
+
+  if (two_branches && sd) GPS_TRY(sd->join(st));
 
   // ---- s = norm1_local(x_loc) + norm1_attn(hA)   (gps_layer.py:194,217,222)
   {
@@ -527,6 +598,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
               (long long)a->workspace_bytes, (long long)P.bwd_bytes);
   GPS_TRY(check_params(a, P));
   GPS_REQUIRE(a->training, GPS_ERR_UNSUPPORTED, "backward is implemented for training mode (batch statistics)");
+  g_grads_prezeroed = (a->reserved0 & 1) != 0;
   GPS_REQUIRE(a->grad_x_out && a->grad_x, GPS_ERR_ARG, "grad_x_out / grad_x are required");
   const int64_t N = P.N, E = P.E, d = P.d;
   const int act = a->act, prec = a->precision;
@@ -541,6 +613,10 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   DropCfg nodrop;
   auto sums = [&](int which) { return P.bsums + (int64_t)which * 2 * d; };
   GPS_CUDA(cudaMemsetAsync(P.bsums, 0, (size_t)BN_COUNT * 2 * d * sizeof(double), st));
+  // weight-gradient GEMMs run on the side stream, each forked where its operands become final
+  Side* sd = side_stream();
+  cudaStream_t s2 = sd ? sd->s : st;
+  auto wfork = [&]() -> int { return sd ? sd->fork(st) : GPS_OK; };
 
   // ---- norm2 (gps_layer.py:229): g_t
   BnView v2 = bn_view(P, BN_2, a->norm2);
@@ -563,8 +639,9 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g.p_drop = pd; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_FF1; g.precision = prec;
     g.offset_dev = (const unsigned long long*)a->offset_dev;
     GPS_TRY(gemm(g, st));
-    GPS_TRY(linear_wgrad(g_ff2, d, P.hid, 2 * d, N, d, 2 * d, a->ff2.grad_weight, a->ff2.grad_bias, prec, st));
-    GPS_TRY(linear_wgrad(P.g_hid, 2 * d, P.s, d, N, 2 * d, d, a->ff1.grad_weight, a->ff1.grad_bias, prec, st));
+    GPS_TRY(wfork());
+    GPS_TRY(linear_wgrad(g_ff2, d, P.hid, 2 * d, N, d, 2 * d, a->ff2.grad_weight, a->ff2.grad_bias, prec, s2));
+    GPS_TRY(linear_wgrad(P.g_hid, 2 * d, P.s, d, N, 2 * d, d, a->ff1.grad_weight, a->ff1.grad_bias, prec, s2));
     GemmParams g2;  // g_s = g_t + g_hid W1
     g2.M = (int)N; g2.N = (int)d; g2.K = (int)(2 * d);
     g2.A = P.g_hid; g2.lda = (int)(2 * d); g2.B = a->ff1.weight; g2.ldb = (int)d; g2.tb = 1; g2.C = P.g_s; g2.ldc = (int)d;
@@ -588,15 +665,16 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     // hA = x + drop(O Wo^T + bo)
     const float* g_ao = P.g_hA;
     if (pd > 0.f) {
-      GPS_TRY(dropmul(P.g_hA, P.g_tmp, N, d, P, a, GPS_SITE_ATTN_OUT, st));
-      g_ao = P.g_tmp;
+      GPS_TRY(dropmul(P.g_hA, P.g_tmp2, N, d, P, a, GPS_SITE_ATTN_OUT, st));
+      g_ao = P.g_tmp2;
     }
     GemmParams g;  // g_O = g_ao Wo
     g.M = (int)N; g.N = (int)d; g.K = (int)d;
     g.A = g_ao; g.lda = (int)d; g.B = a->attn_out.weight; g.ldb = (int)d; g.tb = 1; g.C = P.g_O; g.ldc = (int)d;
     g.precision = prec;
     GPS_TRY(gemm(g, st));
-    GPS_TRY(linear_wgrad(g_ao, d, P.O, d, N, d, d, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, st));
+    GPS_TRY(wfork());
+    GPS_TRY(linear_wgrad(g_ao, d, P.O, d, N, d, d, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, s2));
     const float* Q = P.Y1 + P.qkv_off;
     float* gQ = P.gY1 + P.qkv_off;
     GPS_TRY(attention_bwd(a->graph, P.H, P.hd, Q, Q + d, Q + 2 * d, P.Wy, P.O, P.g_O, d, P.lse, P.delta, gQ, gQ + d,
@@ -611,15 +689,16 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
                          a->norm1_attn.grad_bias, st));
     const float* g_ao = P.g_hA;   // hA = x + drop(to_out(O))
     if (pd > 0.f) {
-      GPS_TRY(dropmul(P.g_hA, P.g_tmp, N, d, P, a, GPS_SITE_ATTN_OUT, st));
-      g_ao = P.g_tmp;
+      GPS_TRY(dropmul(P.g_hA, P.g_tmp2, N, d, P, a, GPS_SITE_ATTN_OUT, st));
+      g_ao = P.g_tmp2;
     }
     GemmParams g;  // g_O = g_ao Wout   [N, inner]
     g.M = (int)N; g.N = (int)inner; g.K = (int)d;
     g.A = g_ao; g.lda = (int)d; g.B = a->attn_out.weight; g.ldb = (int)inner; g.tb = 1; g.C = P.g_O; g.ldc = (int)inner;
     g.precision = prec;
     GPS_TRY(gemm(g, st));
-    GPS_TRY(linear_wgrad(g_ao, d, P.O, inner, N, d, inner, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, st));
+    GPS_TRY(wfork());
+    GPS_TRY(linear_wgrad(g_ao, d, P.O, inner, N, d, inner, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, s2));
     // linear attention and feature maps (performer_layer.py:200-205, 119-144)
     GPS_TRY(perf_linattn_bwd(a->graph, P.H, P.m, P.pnmax, P.pfq, P.pfk, P.pV, P.pgmax, P.g_O, P.g_pfq, P.g_pfk, P.g_pV,
                              P.g_pgmax, st));
@@ -637,8 +716,9 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     // projections: dW = g^T x ;  g_xp = g_hA + gQ Wq + gK Wk + gV Wv
     const GpsLinear* lin[3] = {&a->perf_q, &a->perf_k, &a->perf_v};
     const float* gsrc[3] = {P.g_pQ, P.g_pK, P.g_pV};
+    GPS_TRY(wfork());
     for (int i = 0; i < 3; ++i) {
-      GPS_TRY(linear_wgrad(gsrc[i], inner, a->x, d, N, inner, d, lin[i]->grad_weight, nullptr, prec, st));
+      GPS_TRY(linear_wgrad(gsrc[i], inner, a->x, d, N, inner, d, lin[i]->grad_weight, nullptr, prec, s2));
       GemmParams h;
       h.M = (int)N; h.N = (int)d; h.K = (int)inner;
       h.A = gsrc[i]; h.lda = (int)inner; h.B = lin[i]->weight; h.ldb = (int)d; h.tb = 1; h.C = P.g_xp; h.ldc = (int)d;
@@ -669,7 +749,8 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(gatedgcn_bwd_dst(a->graph, d, P.gY1, P.Wy, P.ehat, P.Y1 + d, P.Wy, P.g_e, P.g_num, P.gY1 + 2 * d, st));
     GPS_TRY(gatedgcn_bwd_src(a->graph, d, P.g_e, P.ehat, P.g_num, P.gY1 + 3 * d, P.gY1 + d, P.Wy, st));
     // C: dC = g_e^T e ; g_edge_attr = grad_edge_out + g_e C
-    GPS_TRY(linear_wgrad(P.g_e, d, a->edge_attr, d, E, d, d, a->gcn_C.grad_weight, a->gcn_C.grad_bias, prec, st));
+    GPS_TRY(wfork());
+    GPS_TRY(linear_wgrad(P.g_e, d, a->edge_attr, d, E, d, d, a->gcn_C.grad_weight, a->gcn_C.grad_bias, prec, s2));
     if (a->grad_edge_attr && E > 0) {
       GemmParams g;
       g.M = (int)E; g.N = (int)d; g.K = (int)d;
@@ -682,8 +763,8 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     // x_loc = x + drop(h1 W1^T + b1)
     const float* g_l1 = P.g_xloc;
     if (pd > 0.f) {
-      GPS_TRY(dropmul(P.g_xloc, P.g_tmp, N, d, P, a, GPS_SITE_LOCAL, st));
-      g_l1 = P.g_tmp;
+      GPS_TRY(dropmul(P.g_xloc, P.g_tmp3, N, d, P, a, GPS_SITE_LOCAL, st));
+      g_l1 = P.g_tmp3;
     }
     GemmParams g;  // g_h1 = (g_l1 W1) * act'(pre)
     g.M = (int)N; g.N = (int)d; g.K = (int)d;
@@ -691,8 +772,9 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     if (relu) { g.mask_src = P.h1; g.mask_is_post = 1; } else { g.mask_src = P.h1_pre; g.mask_act = act; }
     g.ldmask = (int)d; g.precision = prec;
     GPS_TRY(gemm(g, st));
-    GPS_TRY(linear_wgrad(g_l1, d, P.h1, d, N, d, d, a->gine_lin1.grad_weight, a->gine_lin1.grad_bias, prec, st));
-    GPS_TRY(linear_wgrad(P.g_h1, d, P.agg, d, N, d, d, a->gine_lin0.grad_weight, a->gine_lin0.grad_bias, prec, st));
+    GPS_TRY(wfork());
+    GPS_TRY(linear_wgrad(g_l1, d, P.h1, d, N, d, d, a->gine_lin1.grad_weight, a->gine_lin1.grad_bias, prec, s2));
+    GPS_TRY(linear_wgrad(P.g_h1, d, P.agg, d, N, d, d, a->gine_lin0.grad_weight, a->gine_lin0.grad_bias, prec, s2));
     GemmParams g2;  // g_agg = g_h1 W0
     g2.M = (int)N; g2.N = (int)d; g2.K = (int)d;
     g2.A = P.g_h1; g2.lda = (int)d; g2.B = a->gine_lin0.weight; g2.ldb = (int)d; g2.tb = 1; g2.C = P.g_agg; g2.ldc = (int)d;
@@ -706,16 +788,16 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
 
   // ---- g_x = [local paths] + [attention residual] + gY1 Wcat ;  d{A,B,D,E,in_proj}
   if (P.Wy) {
-    GPS_CUDA(cudaMemsetAsync(P.gWcat, 0, (size_t)(P.Wy * d) * sizeof(float), st));
-    GPS_CUDA(cudaMemsetAsync(P.gbcat, 0, (size_t)P.Wy * sizeof(float), st));
+    GPS_TRY(wfork());
+    GPS_CUDA(cudaMemsetAsync(P.gWcat, 0, (size_t)(P.Wy * d + P.Wy) * sizeof(float), s2));
     GemmParams w;
     w.M = (int)P.Wy; w.N = (int)d; w.K = (int)N;
     w.A = P.gY1; w.lda = (int)P.Wy; w.ta = 1; w.B = a->x; w.ldb = (int)d; w.tb = 1; w.C = P.gWcat; w.ldc = (int)d;
     w.splitk = splitk_for(N) < 2 ? 2 : splitk_for(N);
     w.colsum_a = P.gbcat; w.precision = prec;
-    if (N > 0) GPS_TRY(gemm(w, st));
+    if (N > 0) GPS_TRY(gemm(w, s2));
     PackDesc pdsc = pack_desc(a, P);
-    k_unpack<<<kNumSMs * 2, 256, 0, st>>>(pdsc, P.gWcat, P.gbcat);
+    k_unpack<<<(unsigned)pdsc.total_rows, 128, 0, s2>>>(pdsc, P.gWcat, P.gbcat);
     GPS_LAUNCH_CHECK();
     GemmParams g;
     g.M = (int)N; g.N = (int)d; g.K = (int)P.Wy;
@@ -729,6 +811,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   } else {
     GPS_TRY(add3(P.g_xp, d, nullptr, 0, nullptr, 0, a->grad_x, d, N, d, st));   // Performer only
   }
+  if (sd) GPS_TRY(sd->join(st));
   return GPS_OK;
 }
 

@@ -26,8 +26,16 @@ static int node_geom(int64_t N, int64_t d, int nstat, NodeGeom* g) {
               "sparse stage needs d %% 4 == 0 and d <= 4096 (got %lld)", (long long)d);
   int C4 = (int)(d / 4);
   int RY = C4 >= 256 ? 1 : 256 / C4;
+  int64_t cap = kNumSMs * 16;
+  if (nstat > 0) {   // statistics epilogue: same-address double atomics serialise -> few, fat CTAs (see elementwise.cu)
+    RY = C4 >= 1024 ? 1 : 1024 / C4;
+    if (RY > 16) RY = 16;
+    const int smem_cap = (int)(48 * 1024 / ((size_t)nstat * C4 * sizeof(float4)));   // static 48 KB limit
+    if (RY > smem_cap) RY = smem_cap < 1 ? 1 : smem_cap;
+    cap = kNumSMs;
+  }
   int64_t blocks = ceil_div(N > 0 ? N : 1, (int64_t)RY * 2);
-  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  if (blocks > cap) blocks = cap;
   g->block = dim3(C4, RY, 1);
   g->grid = dim3((unsigned)blocks, 1, 1);
   g->smem = RY > 1 ? (size_t)nstat * RY * C4 * sizeof(float4) : 0;
@@ -66,7 +74,7 @@ __device__ __forceinline__ void block_stats(float4* acc, double* const* ptrs, fl
 }
 
 template <bool STATS>
-__global__ void k_gatedgcn_fwd(GpsGraph g, int d, const float* __restrict__ Ax, const float* __restrict__ Bx,
+__global__ void __launch_bounds__(1024) k_gatedgcn_fwd(GpsGraph g, int d, const float* __restrict__ Ax, const float* __restrict__ Bx,
                                const float* __restrict__ Dx, const float* __restrict__ Ex, int64_t ldy,
                                float* __restrict__ Ce, float* __restrict__ xt, double* stats_x,
                                double* stats_e) {
@@ -77,20 +85,34 @@ __global__ void k_gatedgcn_fwd(GpsGraph g, int d, const float* __restrict__ Ax, 
     const float4 dx = ld4(Dx + i * ldy + c);
     float4 num = f4zero(), den = f4zero();
     const int kb = g.dst_ptr[i], ke = g.dst_ptr[i + 1];
-    for (int k = kb; k < ke; ++k) {
-      const int j = g.dst_src[k];
-      const int64_t eid = g.dst_eid[k];
-      const float4 ex = ld4(Ex + (int64_t)j * ldy + c);
-      const float4 bx = ld4(Bx + (int64_t)j * ldy + c);
-      float4 e = ld4(Ce + eid * d + c);
-      e = f4add(e, f4add(dx, ex));
-      st4(Ce + eid * d + c, e);
-      const float4 s = sigmoid4(e);
-      num = f4fma(s, bx, num);
-      den = f4add(den, s);
+    // two edges per iteration: 6 independent 128-bit gathers in flight per thread (the loop is latency bound)
+    for (int k = kb; k < ke; k += 2) {
+      const bool two = k + 1 < ke;
+      const int j0 = g.dst_src[k], j1 = two ? g.dst_src[k + 1] : j0;
+      const int64_t e0 = g.dst_eid[k], e1 = two ? g.dst_eid[k + 1] : e0;
+      const float4 ex0 = ld4(Ex + (int64_t)j0 * ldy + c), bx0 = ld4(Bx + (int64_t)j0 * ldy + c);
+      float4 c0 = ld4(Ce + e0 * d + c);
+      const float4 ex1 = ld4(Ex + (int64_t)j1 * ldy + c), bx1 = ld4(Bx + (int64_t)j1 * ldy + c);
+      float4 c1 = ld4(Ce + e1 * d + c);
+      c0 = f4add(c0, f4add(dx, ex0));
+      st4(Ce + e0 * d + c, c0);
+      const float4 s0 = sigmoid4(c0);
+      num = f4fma(s0, bx0, num);
+      den = f4add(den, s0);
       if (STATS) {
-        acc[2] = f4add(acc[2], e);
-        acc[3] = f4fma(e, e, acc[3]);
+        acc[2] = f4add(acc[2], c0);
+        acc[3] = f4fma(c0, c0, acc[3]);
+      }
+      if (two) {
+        c1 = f4add(c1, f4add(dx, ex1));
+        st4(Ce + e1 * d + c, c1);
+        const float4 s1 = sigmoid4(c1);
+        num = f4fma(s1, bx1, num);
+        den = f4add(den, s1);
+        if (STATS) {
+          acc[2] = f4add(acc[2], c1);
+          acc[3] = f4fma(c1, c1, acc[3]);
+        }
       }
     }
     const float4 ax = ld4(Ax + i * ldy + c);

@@ -165,7 +165,9 @@ class _GPSLayerFn(torch.autograd.Function):
         dev = x.device
         named = dict(zip(layer._param_names, params))
         grads = {n: torch.empty_like(p) for n, p in named.items()}
+        torch._foreach_zero_(list(grads.values()))   # one multi-tensor fill; the library then skips its memsets
         args = layer._base_args(gs, named, grads)
+        args.reserved0 = 1
         args.seed, args.offset, args.training = ctx.seed, ctx.offset, 1
         if ctx.snap is not None:
             args.offset_dev = ctx.snap.data_ptr()
