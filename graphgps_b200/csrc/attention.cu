@@ -130,26 +130,34 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_fwd(AttnArgs a) {
   const bool use_drop = a.p_drop > 0.f;
   DropQuad dq;
   drop_quad_init(dq, a.p_drop);
+  // software pipeline: the K/V rows of key jl+1 are in flight while key jl is processed (the loop is a chain of
+  // load -> dot -> shuffle -> exp -> fma, i.e. latency bound at these tiny graph sizes)
+  float4 kc[CH], vc[CH];
+  load_slice<CH, LPR>(kc, a.K + (int64_t)gs * a.ld + hoff, sub, nch, n > 0);
+  load_slice<CH, LPR>(vc, a.V + (int64_t)gs * a.ld + hoff, sub, nch, n > 0);
   for (int jl = 0; jl < nloop; ++jl) {
     if (use_drop && (jl & 3) == 0) drop_quad_refresh(dq, a.p_drop, a.seed, offs, h, i, jl);
     const bool valid = jl < n;
-    const int j = gs + (valid ? jl : 0);
-    float4 kv[CH];
-    load_slice<CH, LPR>(kv, a.K + (int64_t)j * a.ld + hoff, sub, nch, valid);
-    float s = group_sum<LPR>(dot_slice<CH>(q, kv));
+    const bool nvalid = jl + 1 < n;
+    const int jn = gs + (nvalid ? jl + 1 : 0);
+    float4 kn[CH], vn[CH];
+    load_slice<CH, LPR>(kn, a.K + (int64_t)jn * a.ld + hoff, sub, nch, nvalid);
+    load_slice<CH, LPR>(vn, a.V + (int64_t)jn * a.ld + hoff, sub, nch, nvalid);
+    float s = group_sum<LPR>(dot_slice<CH>(q, kc));
     s = valid ? s : -INFINITY;
     const float m_new = fmaxf(m, s);
     const float corr = (m_new == -INFINITY) ? 1.f : __expf(m - m_new);
     const float p = valid ? __expf(s - m_new) : 0.f;
     l = l * corr + p;
     const float pd = use_drop ? p * drop_quad_scale(dq, jl) : p;
-    load_slice<CH, LPR>(kv, a.V + (int64_t)j * a.ld + hoff, sub, nch, valid);
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      o[c].x = o[c].x * corr + pd * kv[c].x;
-      o[c].y = o[c].y * corr + pd * kv[c].y;
-      o[c].z = o[c].z * corr + pd * kv[c].z;
-      o[c].w = o[c].w * corr + pd * kv[c].w;
+      o[c].x = o[c].x * corr + pd * vc[c].x;
+      o[c].y = o[c].y * corr + pd * vc[c].y;
+      o[c].z = o[c].z * corr + pd * vc[c].z;
+      o[c].w = o[c].w * corr + pd * vc[c].w;
+      kc[c] = kn[c];
+      vc[c] = vn[c];
     }
     m = m_new;
   }
@@ -199,13 +207,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_q(AttnArgs a) 
     const bool use_drop = a.p_drop > 0.f;
     DropQuad dq;
     drop_quad_init(dq, a.p_drop);
+    float4 kk[CH], vv[CH];
+    load_slice<CH, LPR>(kk, a.K + (int64_t)gs * a.ld + hoff, sub, nch, n > 0);
+    load_slice<CH, LPR>(vv, a.V + (int64_t)gs * a.ld + hoff, sub, nch, n > 0);
     for (int jl = 0; jl < nloop; ++jl) {
       if (use_drop && (jl & 3) == 0) drop_quad_refresh(dq, a.p_drop, a.seed, offs, h, i, jl);
       const bool valid = jl < n;
-      const int j = gs + (valid ? jl : 0);
-      float4 kk[CH], vv[CH];
-      load_slice<CH, LPR>(kk, a.K + (int64_t)j * a.ld + hoff, sub, nch, valid);
-      load_slice<CH, LPR>(vv, a.V + (int64_t)j * a.ld + hoff, sub, nch, valid);
+      const bool nvalid = jl + 1 < n;
+      const int jn = gs + (nvalid ? jl + 1 : 0);
+      float4 kn[CH], vn[CH];
+      load_slice<CH, LPR>(kn, a.K + (int64_t)jn * a.ld + hoff, sub, nch, nvalid);
+      load_slice<CH, LPR>(vn, a.V + (int64_t)jn * a.ld + hoff, sub, nch, nvalid);
       float s = dot_slice<CH>(q, kk), dp = dot_slice<CH>(go, vv);
 #pragma unroll
       for (int ofs = LPR / 2; ofs > 0; ofs >>= 1) {
@@ -220,6 +232,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_q(AttnArgs a) 
         gq[c].y += ds * kk[c].y;
         gq[c].z += ds * kk[c].z;
         gq[c].w += ds * kk[c].w;
+        kk[c] = kn[c];
+        vv[c] = vn[c];
       }
     }
   }
@@ -259,12 +273,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_kv(AttnArgs a)
     gk[c] = f4zero();
     gv[c] = f4zero();
   }
+  float4 q[CH], go[CH];
+  load_slice<CH, LPR>(q, a.Q + (int64_t)gs * a.ld + hoff, sub, nch, n > 0);
+  load_slice<CH, LPR>(go, a.dO + (int64_t)gs * a.ldo + hoff, sub, nch, n > 0);
   for (int il = 0; il < nloop; ++il) {
     const bool valid = il < n;
     const int i = gs + (valid ? il : 0);
-    float4 q[CH], go[CH];
-    load_slice<CH, LPR>(q, a.Q + (int64_t)i * a.ld + hoff, sub, nch, valid);
-    load_slice<CH, LPR>(go, a.dO + (int64_t)i * a.ldo + hoff, sub, nch, valid);
+    const bool nvalid = il + 1 < n;
+    const int in_ = gs + (nvalid ? il + 1 : 0);
+    float4 qn[CH], gon[CH];
+    load_slice<CH, LPR>(qn, a.Q + (int64_t)in_ * a.ld + hoff, sub, nch, nvalid);
+    load_slice<CH, LPR>(gon, a.dO + (int64_t)in_ * a.ldo + hoff, sub, nch, nvalid);
     float s = dot_slice<CH>(q, kk), dp = dot_slice<CH>(go, vv);
 #pragma unroll
     for (int ofs = LPR / 2; ofs > 0; ofs >>= 1) {
@@ -287,6 +306,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_kv(AttnArgs a)
     for (int c = 0; c < CH; ++c) {
       gk[c].x += ds * q[c].x; gk[c].y += ds * q[c].y; gk[c].z += ds * q[c].z; gk[c].w += ds * q[c].w;
       gv[c].x += pd * go[c].x; gv[c].y += pd * go[c].y; gv[c].z += pd * go[c].z; gv[c].w += pd * go[c].w;
+      q[c] = qn[c];
+      go[c] = gon[c];
     }
   }
   if (row_ok) {

@@ -70,29 +70,27 @@ namespace {
 // and every weight-gradient GEMM next to the data-gradient chain.  Fork = event on the caller's stream that the
 // side stream waits on; join = the reverse.  All of it is capturable into a CUDA graph.
 struct Side {
-  cudaStream_t s = nullptr;
+  cudaStream_t s = nullptr;    // weight gradients / edge projection / forward attention branch
+  cudaStream_t s3 = nullptr;   // backward attention branch (next to the message-passing backward)
   cudaEvent_t ev[32];
   int next = 0;
   bool ok = false;
   int init() {
     if (ok) return GPS_OK;
     GPS_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    GPS_CUDA(cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking));
     for (int i = 0; i < 32; ++i) GPS_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
     ok = true;
     return GPS_OK;
   }
-  int fork(cudaStream_t main) {   // side waits for everything enqueued on main so far
+  int order(cudaStream_t from, cudaStream_t to) {   // `to` waits for everything enqueued on `from` so far
     cudaEvent_t e = ev[next++ & 31];
-    GPS_CUDA(cudaEventRecord(e, main));
-    GPS_CUDA(cudaStreamWaitEvent(s, e, 0));
+    GPS_CUDA(cudaEventRecord(e, from));
+    GPS_CUDA(cudaStreamWaitEvent(to, e, 0));
     return GPS_OK;
   }
-  int join(cudaStream_t main) {   // main waits for everything enqueued on side so far
-    cudaEvent_t e = ev[next++ & 31];
-    GPS_CUDA(cudaEventRecord(e, s));
-    GPS_CUDA(cudaStreamWaitEvent(main, e, 0));
-    return GPS_OK;
-  }
+  int fork(cudaStream_t main) { return order(main, s); }
+  int join(cudaStream_t main) { return order(s, main); }
 };
 
 static Side* side_stream() {
@@ -616,7 +614,9 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   // weight-gradient GEMMs run on the side stream, each forked where its operands become final
   Side* sd = side_stream();
   cudaStream_t s2 = sd ? sd->s : st;
-  auto wfork = [&]() -> int { return sd ? sd->fork(st) : GPS_OK; };
+  auto wfork = [&](cudaStream_t from) -> int { return sd ? sd->order(from, s2) : GPS_OK; };
+  const bool two_branches = (P.gated || P.gine) && (P.attn || P.perf);
+  cudaStream_t sa = (two_branches && sd) ? sd->s3 : st;   // stream of the attention-branch backward
 
   // ---- norm2 (gps_layer.py:229): g_t
   BnView v2 = bn_view(P, BN_2, a->norm2);
@@ -639,7 +639,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g.p_drop = pd; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_FF1; g.precision = prec;
     g.offset_dev = (const unsigned long long*)a->offset_dev;
     GPS_TRY(gemm(g, st));
-    GPS_TRY(wfork());
+    GPS_TRY(wfork(st));
     GPS_TRY(linear_wgrad(g_ff2, d, P.hid, 2 * d, N, d, 2 * d, a->ff2.grad_weight, a->ff2.grad_bias, prec, s2));
     GPS_TRY(linear_wgrad(P.g_hid, 2 * d, P.s, d, N, 2 * d, d, a->ff1.grad_weight, a->ff1.grad_bias, prec, s2));
     GemmParams g2;  // g_s = g_t + g_hid W1
@@ -657,53 +657,54 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(bn_bwd_apply(P.g_s, d, P.xloc, d, N, d, v, -1, nodrop, sums(BN_L), P.g_xloc, d,
                          a->norm1_local.grad_weight, a->norm1_local.grad_bias, st));
   }
+  if (two_branches && sd) GPS_TRY(sd->order(st, sa));   // attention-branch backward runs next to the local-model backward
   if (P.attn) {
     BnView v = bn_view(P, BN_A, a->norm1_attn);
-    GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), st));
+    GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), sa));
     GPS_TRY(bn_bwd_apply(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), P.g_hA, d, a->norm1_attn.grad_weight,
-                         a->norm1_attn.grad_bias, st));
+                         a->norm1_attn.grad_bias, sa));
     // hA = x + drop(O Wo^T + bo)
     const float* g_ao = P.g_hA;
     if (pd > 0.f) {
-      GPS_TRY(dropmul(P.g_hA, P.g_tmp2, N, d, P, a, GPS_SITE_ATTN_OUT, st));
+      GPS_TRY(dropmul(P.g_hA, P.g_tmp2, N, d, P, a, GPS_SITE_ATTN_OUT, sa));
       g_ao = P.g_tmp2;
     }
     GemmParams g;  // g_O = g_ao Wo
     g.M = (int)N; g.N = (int)d; g.K = (int)d;
     g.A = g_ao; g.lda = (int)d; g.B = a->attn_out.weight; g.ldb = (int)d; g.tb = 1; g.C = P.g_O; g.ldc = (int)d;
     g.precision = prec;
-    GPS_TRY(gemm(g, st));
-    GPS_TRY(wfork());
+    GPS_TRY(gemm(g, sa));
+    GPS_TRY(wfork(sa));
     GPS_TRY(linear_wgrad(g_ao, d, P.O, d, N, d, d, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, s2));
     const float* Q = P.Y1 + P.qkv_off;
     float* gQ = P.gY1 + P.qkv_off;
     GPS_TRY(attention_bwd(a->graph, P.H, P.hd, Q, Q + d, Q + 2 * d, P.Wy, P.O, P.g_O, d, P.lse, P.delta, gQ, gQ + d,
-                          gQ + 2 * d, P.Wy, pa, a->seed, a->offset, st, (const unsigned long long*)a->offset_dev));
+                          gQ + 2 * d, P.Wy, pa, a->seed, a->offset, sa, (const unsigned long long*)a->offset_dev));
   }
 
   if (P.perf) {
     const int64_t inner = P.inner, NH = N * P.H, dh = a->perf_dim_head;
     BnView v = bn_view(P, BN_A, a->norm1_attn);
-    GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), st));
+    GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), sa));
     GPS_TRY(bn_bwd_apply(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), P.g_hA, d, a->norm1_attn.grad_weight,
-                         a->norm1_attn.grad_bias, st));
+                         a->norm1_attn.grad_bias, sa));
     const float* g_ao = P.g_hA;   // hA = x + drop(to_out(O))
     if (pd > 0.f) {
-      GPS_TRY(dropmul(P.g_hA, P.g_tmp2, N, d, P, a, GPS_SITE_ATTN_OUT, st));
+      GPS_TRY(dropmul(P.g_hA, P.g_tmp2, N, d, P, a, GPS_SITE_ATTN_OUT, sa));
       g_ao = P.g_tmp2;
     }
     GemmParams g;  // g_O = g_ao Wout   [N, inner]
     g.M = (int)N; g.N = (int)inner; g.K = (int)d;
     g.A = g_ao; g.lda = (int)d; g.B = a->attn_out.weight; g.ldb = (int)inner; g.tb = 1; g.C = P.g_O; g.ldc = (int)inner;
     g.precision = prec;
-    GPS_TRY(gemm(g, st));
-    GPS_TRY(wfork());
+    GPS_TRY(gemm(g, sa));
+    GPS_TRY(wfork(sa));
     GPS_TRY(linear_wgrad(g_ao, d, P.O, inner, N, d, inner, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, s2));
     // linear attention and feature maps (performer_layer.py:200-205, 119-144)
     GPS_TRY(perf_linattn_bwd(a->graph, P.H, P.m, P.pnmax, P.pfq, P.pfk, P.pV, P.pgmax, P.g_O, P.g_pfq, P.g_pfk, P.g_pV,
-                             P.g_pgmax, st));
+                             P.g_pgmax, sa));
     GPS_TRY(perf_features_bwd(P.g_pfq, P.g_pfk, P.pfq, P.pfk, P.pQ, P.pK, P.g_pQ, P.g_pK, a->graph, P.H, P.m, P.pargq,
-                              P.pargk, P.g_pgmax, st));
+                              P.pargk, P.g_pgmax, sa));
     float* gdd[2] = {P.g_pfq, P.g_pfk};
     float* gqk[2] = {P.g_pQ, P.g_pK};
     for (int i = 0; i < 2; ++i) {   // g_q += g_dd Pn   (dd = q Pn^T)
@@ -711,19 +712,19 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
       h.M = (int)NH; h.N = (int)dh; h.K = (int)P.mp;
       h.A = gdd[i]; h.lda = (int)P.mp; h.B = P.pPn; h.ldb = (int)dh; h.tb = 1; h.C = gqk[i]; h.ldc = (int)dh;
       h.R1 = gqk[i]; h.ldr1 = (int)dh; h.precision = prec;
-      GPS_TRY(gemm(h, st));
+      GPS_TRY(gemm(h, sa));
     }
     // projections: dW = g^T x ;  g_xp = g_hA + gQ Wq + gK Wk + gV Wv
     const GpsLinear* lin[3] = {&a->perf_q, &a->perf_k, &a->perf_v};
     const float* gsrc[3] = {P.g_pQ, P.g_pK, P.g_pV};
-    GPS_TRY(wfork());
+    GPS_TRY(wfork(sa));
     for (int i = 0; i < 3; ++i) {
       GPS_TRY(linear_wgrad(gsrc[i], inner, a->x, d, N, inner, d, lin[i]->grad_weight, nullptr, prec, s2));
       GemmParams h;
       h.M = (int)N; h.N = (int)d; h.K = (int)inner;
       h.A = gsrc[i]; h.lda = (int)inner; h.B = lin[i]->weight; h.ldb = (int)d; h.tb = 1; h.C = P.g_xp; h.ldc = (int)d;
       h.R1 = i == 0 ? P.g_hA : P.g_xp; h.ldr1 = (int)d; h.precision = prec;
-      GPS_TRY(gemm(h, st));
+      GPS_TRY(gemm(h, sa));
     }
   }
 
@@ -749,7 +750,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(gatedgcn_bwd_dst(a->graph, d, P.gY1, P.Wy, P.ehat, P.Y1 + d, P.Wy, P.g_e, P.g_num, P.gY1 + 2 * d, st));
     GPS_TRY(gatedgcn_bwd_src(a->graph, d, P.g_e, P.ehat, P.g_num, P.gY1 + 3 * d, P.gY1 + d, P.Wy, st));
     // C: dC = g_e^T e ; g_edge_attr = grad_edge_out + g_e C
-    GPS_TRY(wfork());
+    GPS_TRY(wfork(st));
     GPS_TRY(linear_wgrad(P.g_e, d, a->edge_attr, d, E, d, d, a->gcn_C.grad_weight, a->gcn_C.grad_bias, prec, s2));
     if (a->grad_edge_attr && E > 0) {
       GemmParams g;
@@ -772,7 +773,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     if (relu) { g.mask_src = P.h1; g.mask_is_post = 1; } else { g.mask_src = P.h1_pre; g.mask_act = act; }
     g.ldmask = (int)d; g.precision = prec;
     GPS_TRY(gemm(g, st));
-    GPS_TRY(wfork());
+    GPS_TRY(wfork(st));
     GPS_TRY(linear_wgrad(g_l1, d, P.h1, d, N, d, d, a->gine_lin1.grad_weight, a->gine_lin1.grad_bias, prec, s2));
     GPS_TRY(linear_wgrad(P.g_h1, d, P.agg, d, N, d, d, a->gine_lin0.grad_weight, a->gine_lin0.grad_bias, prec, s2));
     GemmParams g2;  // g_agg = g_h1 W0
@@ -786,9 +787,11 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g_x_local = P.g_xl;
   }
 
+  if (two_branches && sd) GPS_TRY(sd->order(sa, st));
+
   // ---- g_x = [local paths] + [attention residual] + gY1 Wcat ;  d{A,B,D,E,in_proj}
   if (P.Wy) {
-    GPS_TRY(wfork());
+    GPS_TRY(wfork(st));
     GPS_CUDA(cudaMemsetAsync(P.gWcat, 0, (size_t)(P.Wy * d + P.Wy) * sizeof(float), s2));
     GemmParams w;
     w.M = (int)P.Wy; w.N = (int)d; w.K = (int)N;
