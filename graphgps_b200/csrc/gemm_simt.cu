@@ -104,7 +104,14 @@ __global__ void __launch_bounds__(NT) k_gemm_simt(GemmParams p, int kchunk, bool
       if (gm >= p.M) continue;
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        if (gn + j < p.N) atomicAdd(&p.C[(int64_t)gm * p.ldc + gn + j], acc[i][j]);
+        if (gn + j < p.N) {
+          float w = acc[i][j];
+          if (blockIdx.z == 0) {   // the first split also carries the residual terms
+            if (p.R1) w += p.R1[(int64_t)gm * p.ldr1 + gn + j];
+            if (p.R2) w += p.R2[(int64_t)gm * p.ldr2 + gn + j];
+          }
+          atomicAdd(&p.C[(int64_t)gm * p.ldc + gn + j], w);
+        }
     }
     return;
   }
@@ -198,9 +205,8 @@ int gemm_simt(const GemmParams& p, cudaStream_t stream) {
   if (p.M == 0 || p.N == 0) return GPS_OK;
   GPS_REQUIRE(p.splitk >= 1, GPS_ERR_ARG, "gemm: splitk < 1");
   if (p.splitk > 1)
-    GPS_REQUIRE(!p.bias && p.act < 0 && !p.mask_src && !p.R1 && !p.R2 && !p.stats && !p.C_pre &&
-                    p.p_drop == 0.f,
-                GPS_ERR_ARG, "gemm: split-K supports the plain product only");
+    GPS_REQUIRE(!p.bias && p.act < 0 && !p.mask_src && !p.stats && !p.C_pre && p.p_drop == 0.f, GPS_ERR_ARG,
+                "gemm: split-K supports the plain product (+ residuals) only");
   GPS_REQUIRE(p.colsum_a == nullptr || p.ta == 1, GPS_ERR_ARG, "gemm: colsum_a needs ta == 1");
   GPS_REQUIRE(p.p_drop == 0.f || (p.N % 4 == 0), GPS_ERR_ARG, "gemm: dropout epilogue needs N %% 4 == 0");
   int splitk = p.splitk;

@@ -387,8 +387,15 @@ __global__ void __launch_bounds__(kThreads, NBC == 2 ? 2 : 1) k_gemm_tc(const Tc
           if (row_ok) {
             float* dst = p.C + (int64_t)row * p.ldc + gn;
 #pragma unroll
-            for (int e = 0; e < 16; e += 4)   // N % 4 == 0: whole 16-byte groups; red.global.add.v4.f32
-              if (gn + e < p.N) atomicAdd(reinterpret_cast<float4*>(dst + e), make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]));
+            for (int e = 0; e < 16; e += 4) {  // N % 4 == 0: whole 16-byte groups; red.global.add.v4.f32
+              if (gn + e >= p.N) continue;
+              float4 w4 = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+              if (blockIdx.z == 0) {           // the first split also carries the residual terms
+                if (p.R1) w4 = f4add(w4, ld4(p.R1 + (int64_t)row * p.ldr1 + gn + e));
+                if (p.R2) w4 = f4add(w4, ld4(p.R2 + (int64_t)row * p.ldr2 + gn + e));
+              }
+              atomicAdd(reinterpret_cast<float4*>(dst + e), w4);
+            }
           }
           continue;
         }
@@ -482,6 +489,7 @@ __global__ void __launch_bounds__(kThreads, NBC == 2 ? 2 : 1) k_gemm_tc(const Tc
 }
 
 int g_tc_debug = 0;
+int g_tc_force_bn = 0;
 
 inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
@@ -504,7 +512,10 @@ int launch(const TcArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
 
 }  // namespace
 
-void gemm_tc_set_debug(int v) { g_tc_debug = v; }
+void gemm_tc_set_debug(int v) {   // low 4 bits: triage switches; bits 8.. : forced tile width (0 = heuristic)
+  g_tc_debug = v & 0xFF;
+  g_tc_force_bn = (v >> 8) & 0x1FF;
+}
 void gemm_tc_set_trace(long long*) {}
 
 int gemm_tc(const GemmParams& p, cudaStream_t stream) {
@@ -526,8 +537,8 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
     return GPS_ERR_UNSUPPORTED;
   // lean producer loop: whole 8-element chunks are either inside or outside the operand
   if ((!p.ta && p.K % 8) || (!p.tb && p.K % 8) || (p.ta && p.M % 8) || (p.tb && p.N % 8)) return GPS_ERR_UNSUPPORTED;
-  if (p.splitk > 1 && (p.bias || p.act >= 0 || p.mask_src || p.R1 || p.R2 || p.stats || p.C_pre || p.p_drop != 0.f)) {
-    set_error("gemm: split-K supports the plain product only");
+  if (p.splitk > 1 && (p.bias || p.act >= 0 || p.mask_src || p.stats || p.C_pre || p.p_drop != 0.f)) {
+    set_error("gemm: split-K supports the plain product (+ residuals) only");
     return GPS_ERR_ARG;
   }
   if (p.colsum_a && !p.ta) {
@@ -554,6 +565,7 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
     long cost = waves * (BM + nb * 64L);
     if (bestCost < 0 || cost < bestCost) { bestCost = cost; bestBN = bn; }
   }
+  if (g_tc_force_bn > 0) bestBN = g_tc_force_bn;   // tuning hook (tools/gemm_tune.py)
   TcArgs a;
   a.p = p;
   a.BN = bestBN;

@@ -6,11 +6,25 @@
 namespace gps {
 
 // Per-column BatchNorm view used by consumers: y = gamma * (z - mean) * invstd + beta
+// mode 0: mean/invstd arrays are final (backward, or after an explicit bn_finalize)
+// mode 1: training forward — the consumer derives mean/invstd from the producer's double column sums itself and
+//         its first CTA stores them (for backward) and applies torch.nn.BatchNorm1d's running-stat update, so no
+//         separate finalize launch sits between producer and consumer
+// mode 2: eval forward — running statistics
 struct BnView {
   const float* mean = nullptr;
   const float* invstd = nullptr;
   const float* gamma = nullptr;
   const float* beta = nullptr;
+  int mode = 0;
+  const double* sums = nullptr;   // [2][d]
+  double inv_n = 0.0, unbias = 1.0;
+  int64_t d = 0;
+  float* save_mean = nullptr;
+  float* save_invstd = nullptr;
+  float* running_mean = nullptr;
+  float* running_var = nullptr;
+  long long* nbt = nullptr;
 };
 
 struct DropCfg {

@@ -306,6 +306,26 @@ static BnView bn_view(const Plan& P, int which, const GpsBatchNorm& bn) {
   return v;
 }
 
+// forward view: the consumer kernel finalises the statistics itself (BnView mode 1 / 2)
+static BnView bn_view_fwd(const Plan& P, const GpsLayerArgs* a, int which, const GpsBatchNorm& bn, int64_t n) {
+  BnView v = bn_view(P, which, bn);
+  v.d = P.d;
+  v.running_mean = bn.running_mean;
+  v.running_var = bn.running_var;
+  if (a->training) {
+    v.mode = 1;
+    v.sums = P.fstats + (int64_t)which * 2 * P.d;
+    v.inv_n = 1.0 / (double)(n > 0 ? n : 1);
+    v.unbias = n > 1 ? (double)n / (double)(n - 1) : 1.0;
+    v.save_mean = P.bnbuf + (int64_t)which * 2 * P.d;
+    v.save_invstd = v.save_mean + P.d;
+    v.nbt = (long long*)bn.num_batches_tracked;
+  } else {
+    v.mode = 2;
+  }
+  return v;
+}
+
 static int bn_ready(const Plan& P, const GpsLayerArgs* a, int which, const GpsBatchNorm& bn, int64_t n,
                     cudaStream_t st) {
   float* mean = P.bnbuf + (int64_t)which * 2 * P.d;
@@ -381,9 +401,13 @@ static int check_params(const GpsLayerArgs* a, const Plan& P) {
 // (one multi-tensor fill instead of a memset per weight and bias)
 static thread_local bool g_grads_prezeroed = false;
 
-static int splitk_for(int64_t rows) {
-  // reduction over `rows` (nodes/edges) for weight gradients: enough CTAs to fill the machine
-  int64_t s = rows / 256;
+static int splitk_for(int64_t rows, int64_t out = 304, int64_t in = 304) {
+  // Weight gradients reduce over `rows` (nodes/edges) into a small [out, in] tile grid: split the reduction so
+  // that tiles x splits ~ 300 CTAs (two per SM), at least 4 k-blocks of 64 rows per CTA (tools/gemm_tune.py).
+  const int64_t tiles = ceil_div(out, 128) * ceil_div(in, in >= 160 ? 160 : 64);
+  int64_t s = ceil_div(300, tiles > 0 ? tiles : 1);
+  const int64_t max_s = rows / 256;
+  if (s > max_s) s = max_s;
   if (s < 1) s = 1;
   if (s > 64) s = 64;
   return (int)s;
@@ -403,7 +427,7 @@ static int linear_wgrad(const float* G, int64_t ldg, const float* X, int64_t ldx
   p.A = G; p.lda = (int)ldg; p.ta = 1;
   p.B = X; p.ldb = (int)ldx; p.tb = 1;
   p.C = dW; p.ldc = (int)in;
-  p.splitk = splitk_for(rows);
+  p.splitk = splitk_for(rows, out, in);
   if (p.splitk == 1) p.splitk = 2;  // accumulate path (C pre-zeroed) also for tiny inputs
   p.colsum_a = db;
   p.precision = precision;
@@ -454,33 +478,45 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     PackDesc pdsc = pack_desc(a, P);
     k_pack<<<(unsigned)pdsc.total_rows, 128, 0, st>>>(pdsc, P.Wcat, P.bcat);
     GPS_LAUNCH_CHECK();
-    GemmParams g;
-    g.M = (int)N; g.N = (int)P.Wy; g.K = (int)d;
-    g.A = a->x; g.lda = (int)d; g.B = P.Wcat; g.ldb = (int)d; g.C = P.Y1; g.ldc = (int)P.Wy;
-    g.bias = P.bcat; g.precision = a->precision;
-    GPS_TRY(gemm(g, st));
   }
-
-  // main waits for the edge projection; then the global branch forks off the node projections
-  if (P.gated && sd) GPS_TRY(sd->join(st));
+  // The two consumers of the projections get their own GEMM: [Ax|Bx|Dx|Ex] on the main stream for the
+  // message-passing branch, [Q|K|V] on the attention branch's stream, so both branches start ~25 us after the
+  // pack instead of after one 50 us GEMM.
   cudaStream_t sg = st;   // stream of the global-attention branch
   if (two_branches && sd) {
-    GPS_TRY(sd->fork(st));
-    sg = s2;
+    GPS_TRY(sd->order(st, sd->s3));
+    sg = sd->s3;
   }
+  if (P.Wy) {
+    const int64_t wl = P.qkv_off, wg = P.Wy - P.qkv_off;   // local / global column blocks
+    if (wg > 0) {
+      GemmParams g;
+      g.M = (int)N; g.N = (int)wg; g.K = (int)d;
+      g.A = a->x; g.lda = (int)d; g.B = P.Wcat + wl * d; g.ldb = (int)d; g.C = P.Y1 + wl; g.ldc = (int)P.Wy;
+      g.bias = P.bcat + wl; g.precision = a->precision;
+      GPS_TRY(gemm(g, sg));
+    }
+    if (wl > 0) {
+      GemmParams g;
+      g.M = (int)N; g.N = (int)wl; g.K = (int)d;
+      g.A = a->x; g.lda = (int)d; g.B = P.Wcat; g.ldb = (int)d; g.C = P.Y1; g.ldc = (int)P.Wy;
+      g.bias = P.bcat; g.precision = a->precision;
+      GPS_TRY(gemm(g, st));
+    }
+  }
+
+  // main waits for the edge projection
+  if (P.gated && sd) GPS_TRY(sd->join(st));
 
   // ---- local model
   if (P.gated) {
     GPS_TRY(gatedgcn_fwd(a->graph, d, P.Y1, P.Y1 + d, P.Y1 + 2 * d, P.Y1 + 3 * d, P.Wy, P.ehat, P.xt,
                          stats(BN_X), stats(BN_E), st));
-    GPS_TRY(bn_ready(P, a, BN_X, a->bn_node_x, N, st));
-    GPS_TRY(bn_ready(P, a, BN_E, a->bn_edge_e, E, st));
     // x_loc = x + drop(act(BN(x~)));  e_out = e + drop(act(BN(e^)))   (gatedgcn_layer.py:72-83)
-    GPS_TRY(bn_act_residual(P.xt, d, a->x, P.xloc, N, d, bn_view(P, BN_X, a->bn_node_x), act, drop(GPS_SITE_GCN_X),
+    GPS_TRY(bn_act_residual(P.xt, d, a->x, P.xloc, N, d, bn_view_fwd(P, a, BN_X, a->bn_node_x, N), act, drop(GPS_SITE_GCN_X),
                             stats(BN_L), st));
-    GPS_TRY(bn_act_residual(P.ehat, d, a->edge_attr, a->edge_out, E, d, bn_view(P, BN_E, a->bn_edge_e), act,
+    GPS_TRY(bn_act_residual(P.ehat, d, a->edge_attr, a->edge_out, E, d, bn_view_fwd(P, a, BN_E, a->bn_edge_e, E), act,
                             drop(GPS_SITE_GCN_E), nullptr, st));
-    GPS_TRY(bn_ready(P, a, BN_L, a->norm1_local, N, st));
   } else if (P.gine) {
     GPS_TRY(gine_fwd(a->graph, d, a->x, a->edge_attr, a->gine_eps, P.agg, st));
     GemmParams g;  // h1 = act(agg W0^T + b0)
@@ -496,7 +532,6 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g2.offset_dev = (const unsigned long long*)a->offset_dev;
     g2.precision = a->precision;
     GPS_TRY(gemm(g2, st));
-    GPS_TRY(bn_ready(P, a, BN_L, a->norm1_local, N, st));
   }
 
   // ---- global attention  (gps_layer.py:198-218, 234-241)
@@ -512,7 +547,6 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.offset_dev = (const unsigned long long*)a->offset_dev;
     g.precision = a->precision;
     GPS_TRY(gemm(g, sg));
-    GPS_TRY(bn_ready(P, a, BN_A, a->norm1_attn, N, sg));
   }
 
   // ---- Performer global attention (gps_layer.py:205-206; performer_layer.py:476-503)
@@ -546,18 +580,17 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.offset_dev = (const unsigned long long*)a->offset_dev;
     g.precision = a->precision;
     GPS_TRY(gemm(g, sg));
-    GPS_TRY(bn_ready(P, a, BN_A, a->norm1_attn, N, sg));
   }
 
-  if (two_branches && sd) GPS_TRY(sd->join(st));
+  if (two_branches && sd) GPS_TRY(sd->order(sd->s3, st));
 
   // ---- s = norm1_local(x_loc) + norm1_attn(hA)   (gps_layer.py:194,217,222)
   {
     const bool loc = P.gated || P.gine;
     const float* first = loc ? P.xloc : P.hA;
-    BnView bf = loc ? bn_view(P, BN_L, a->norm1_local) : bn_view(P, BN_A, a->norm1_attn);
+    BnView bf = loc ? bn_view_fwd(P, a, BN_L, a->norm1_local, N) : bn_view_fwd(P, a, BN_A, a->norm1_attn, N);
     const float* second = (loc && (P.attn || P.perf)) ? P.hA : nullptr;
-    BnView bs = bn_view(P, BN_A, a->norm1_attn);
+    BnView bs = bn_view_fwd(P, a, BN_A, a->norm1_attn, N);
     GPS_TRY(bn_combine(first, bf, second, bs, P.s, N, d, st));
   }
 
@@ -577,8 +610,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g2.p_drop = pd; g2.seed = a->seed; g2.offset = a->offset; g2.site = GPS_SITE_FF2; g2.precision = a->precision;
     g2.offset_dev = (const unsigned long long*)a->offset_dev;
     GPS_TRY(gemm(g2, st));
-    GPS_TRY(bn_ready(P, a, BN_2, a->norm2, N, st));
-    GPS_TRY(bn_combine(P.t, bn_view(P, BN_2, a->norm2), nullptr, BnView(), a->x_out, N, d, st));  // :229
+    GPS_TRY(bn_combine(P.t, bn_view_fwd(P, a, BN_2, a->norm2, N), nullptr, BnView(), a->x_out, N, d, st));  // :229
   }
   return GPS_OK;
 }
@@ -796,7 +828,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GemmParams w;
     w.M = (int)P.Wy; w.N = (int)d; w.K = (int)N;
     w.A = P.gY1; w.lda = (int)P.Wy; w.ta = 1; w.B = a->x; w.ldb = (int)d; w.tb = 1; w.C = P.gWcat; w.ldc = (int)d;
-    w.splitk = splitk_for(N) < 2 ? 2 : splitk_for(N);
+    w.splitk = splitk_for(N, P.Wy, d) < 2 ? 2 : splitk_for(N, P.Wy, d);
     w.colsum_a = P.gbcat; w.precision = prec;
     if (N > 0) GPS_TRY(gemm(w, s2));
     PackDesc pdsc = pack_desc(a, P);
@@ -808,6 +840,10 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g.R1 = g_x_local; g.ldr1 = (int)d;
     g.R2 = P.attn ? P.g_hA : (P.perf ? P.g_xp : nullptr); g.ldr2 = (int)d;
     g.precision = prec;
+    if (P.Wy >= 1024 && N > 0) {   // long reduction, few output tiles: 2-way split-K fills the machine
+      GPS_CUDA(cudaMemsetAsync(a->grad_x, 0, (size_t)(N * d) * sizeof(float), st));
+      g.splitk = 4;
+    }
     GPS_TRY(gemm(g, st));
   } else if (g_x_local) {
     GPS_TRY(add3(g_x_local, d, P.perf ? P.g_xp : nullptr, d, nullptr, 0, a->grad_x, d, N, d, st));

@@ -48,3 +48,18 @@ print(f"{wl}: sum of kernel time per step = {tot:.1f} us")
 for t, c, k in rows[:28]:
     k = k.replace("gps::(anonymous namespace)::", "").replace("void ", "")
     print(f"{t:9.1f} us {100*t/tot:5.1f}%  n={c:4.1f}  avg={t/c:7.1f}  {k[:90]}")
+
+# ---- timeline of ONE step: (start offset us, duration us, stream, kernel) to see the critical path / overlap
+with profile(activities=[ProfilerActivity.CUDA]) as prof2:
+    step()
+    torch.cuda.synchronize()
+evs = [e for e in prof2.events() if e.device_type is not None and str(e.device_type).endswith("CUDA") and e.time_range is not None]
+evs = [e for e in evs if (e.time_range.end - e.time_range.start) > 0]
+evs.sort(key=lambda e: e.time_range.start)
+if evs:
+    t0 = evs[0].time_range.start
+    print("timeline of one step: start_us dur_us stream name")
+    for e in evs:
+        nm = e.name.replace("gps::(anonymous namespace)::", "").replace("void ", "")[:60]
+        print(f"{e.time_range.start - t0:8.1f} {e.time_range.end - e.time_range.start:7.1f}  s{getattr(e, 'stream', getattr(e, 'device_resource_id', '?'))}  {nm}")
+    print("step span us:", evs[-1].time_range.end - t0)
