@@ -34,6 +34,13 @@ int perf_features_bwd(float* g_fq, float* g_fk, const float* fq, const float* fk
                       float* gQ, float* gK, const GpsGraph& g, int64_t H, int64_t m, const int* argq, const int* argk,
                       float* ggmax, cudaStream_t st);
 
+// performer_quad.cu (pairwise form for batches of small graphs)
+int perf_quad_fwd(const GpsGraph& g, int64_t H, int64_t m, const int* nmax, const float* qf, const float* kf,
+                  const float* V, const float* gmax, float* O, float* den, cudaStream_t st);
+int perf_quad_bwd(const GpsGraph& g, int64_t H, int64_t m, const int* nmax, const float* qf, const float* kf,
+                  const float* V, const float* gmax, const float* O, const float* den, const float* gO, float* gden,
+                  float* g_qf, float* g_kf, float* gV, float* ggmax, cudaStream_t st);
+
 // ------------------------------------------------------------------------------- error plumbing
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
@@ -145,6 +152,8 @@ struct Plan {
   int64_t inner, mp, m;   // Performer: H*64, padded / real feature count
   float *pQ, *pK, *pV, *pfq, *pfk, *pPn, *pgmax;   // saved (Performer)
   int *pargq, *pargk, *pnmax;
+  float *pden, *g_pden;   // pairwise form: denominators (saved) and their gradients
+  bool perf_pairwise;     // mean graph size <= 48: n^2 (m+64) < 2 n m 64
   float *g_pfq, *g_pfk, *g_pQ, *g_pK, *g_pV, *g_pgmax, *g_xp;   // backward workspace (Performer)
   // saved
   float *Wcat, *bcat, *Y1, *ehat, *xt, *xloc, *O, *lse, *hA, *s, *hid, *hid_pre, *t, *bnbuf;
@@ -235,6 +244,8 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
     P->pargq = S.alloc<int>(NH);
     P->pargk = S.alloc<int>(BH);
     P->pnmax = S.alloc<int>(1);
+    P->pden = S.alloc<float>(NH);
+    P->perf_pairwise = a->graph.B > 0 && N <= 48 * a->graph.B;
     P->O = S.alloc<float>(N * P->inner);
     P->hA = S.alloc<float>(N * d);
   }
@@ -277,6 +288,7 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
     P->g_pK = Bk.alloc<float>(N * P->inner);
     P->g_pV = Bk.alloc<float>(N * P->inner);
     P->g_pgmax = Bk.alloc<float>(BH);
+    P->g_pden = Bk.alloc<float>(NH);
     P->g_xp = Bk.alloc<float>(N * d);
   }
   if (P->Wy) {
@@ -571,7 +583,10 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
       GPS_TRY(gemm(g, sg));
     }
     GPS_TRY(perf_features_fwd(P.pfq, P.pfk, P.pQ, P.pK, a->graph, P.H, P.m, P.pgmax, P.pargq, P.pargk, sg));
-    GPS_TRY(perf_linattn_fwd(a->graph, P.H, P.m, P.pnmax, P.pfq, P.pfk, P.pV, P.pgmax, P.O, sg));
+    if (P.perf_pairwise)
+      GPS_TRY(perf_quad_fwd(a->graph, P.H, P.m, P.pnmax, P.pfq, P.pfk, P.pV, P.pgmax, P.O, P.pden, sg));
+    else
+      GPS_TRY(perf_linattn_fwd(a->graph, P.H, P.m, P.pnmax, P.pfq, P.pfk, P.pV, P.pgmax, P.O, sg));
     GemmParams g;  // hA = x + drop(to_out(O))
     g.M = (int)N; g.N = (int)d; g.K = (int)inner;
     g.A = P.O; g.lda = (int)inner; g.B = a->attn_out.weight; g.ldb = (int)inner; g.C = P.hA; g.ldc = (int)d;
@@ -733,8 +748,12 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(wfork(sa));
     GPS_TRY(linear_wgrad(g_ao, d, P.O, inner, N, d, inner, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, s2));
     // linear attention and feature maps (performer_layer.py:200-205, 119-144)
-    GPS_TRY(perf_linattn_bwd(a->graph, P.H, P.m, P.pnmax, P.pfq, P.pfk, P.pV, P.pgmax, P.g_O, P.g_pfq, P.g_pfk, P.g_pV,
-                             P.g_pgmax, sa));
+    if (P.perf_pairwise)
+      GPS_TRY(perf_quad_bwd(a->graph, P.H, P.m, P.pnmax, P.pfq, P.pfk, P.pV, P.pgmax, P.O, P.pden, P.g_O, P.g_pden,
+                            P.g_pfq, P.g_pfk, P.g_pV, P.g_pgmax, sa));
+    else
+      GPS_TRY(perf_linattn_bwd(a->graph, P.H, P.m, P.pnmax, P.pfq, P.pfk, P.pV, P.pgmax, P.g_O, P.g_pfq, P.g_pfk, P.g_pV,
+                               P.g_pgmax, sa));
     GPS_TRY(perf_features_bwd(P.g_pfq, P.g_pfk, P.pfq, P.pfk, P.pQ, P.pK, P.g_pQ, P.g_pK, a->graph, P.H, P.m, P.pargq,
                               P.pargk, P.g_pgmax, sa));
     float* gdd[2] = {P.g_pfq, P.g_pfk};
