@@ -55,18 +55,59 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clock/throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle-reason sampling DURING the timed region (B200_PROFILING.md recipe).
+
+    The timed region of this benchmark is tens of milliseconds, far below nvidia-smi's loop period, so the
+    same counters are read through NVML (nvidia_ml_py) from a thread every ~2 ms; nvidia-smi is the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.lines = index, None, []
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self.thr = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _loop_nvml(self):
+        n = self.nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(n, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    r = int(get_reasons(self.handle))
+                    for name, bit in bits.items():
+                        if r & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.thr = threading.Thread(target=self._loop_nvml, daemon=True)
+            self.thr.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -78,6 +119,13 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            if self.thr is not None:
+                self.thr.join(timeout=1)
+            sm = sorted(self.samples)
+            return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml, 2 ms period"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -101,7 +149,7 @@ class ClockSampler:
                     reasons.add(nm)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 def make_workload(name, seed, device=None):
@@ -461,8 +509,11 @@ def run_ours(args):
 
 
 def roofline_probe(lib, layer, b, spec, heads, args):
-    """Times the step's dominant kernel live: the node-projection GEMM (tensor bound) and the GatedGCN
-    segmented gather-reduce (HBM bound) through their C-ABI stage calls; reports the slower one."""
+    """Times the step's two headline kernels live (CUDA events around their C-ABI stage calls, L2 flushed, host
+    launch latency hidden behind a spin kernel): the longest single kernel of the step — the data-gradient GEMM
+    g_x = gY1[N,7d] . Wcat[7d,d] (tensor bound, 2*N*7d*d flop) — and the GatedGCN gather-reduce (HBM bound,
+    4*(5N+2E)*d algorithmic bytes).  `traffic` = DRAM bytes per launch of the same kernels from the
+    committed `ncu --set full` capture (profiles/r1_roofline_traffic.json)."""
     import ctypes as C
     from graphgps_b200.graph import graph_of
     pk = peaks()
@@ -471,6 +522,10 @@ def roofline_probe(lib, layer, b, spec, heads, args):
     N, E, d = gs.N, gs.E, spec.dim
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
     res = {}
 
     def timeit(fn, reps=10):
@@ -488,19 +543,20 @@ def roofline_probe(lib, layer, b, spec, heads, args):
             tot += e0.elapsed_time(e1)
         return tot / reps * 1e-3
 
-    # (1) node projections [N, 7d] = x [N,d] . Wcat^T : 2*N*7d*d flop
+    prec = 0 if args.precision == "fp32" else 1
     Wy = 7 * d
     W = torch.randn(Wy, d, device=dev) / d ** 0.5
-    bias = torch.zeros(Wy, device=dev)
-    Y = torch.empty(N, Wy, device=dev)
-    prec = 0 if args.precision == "fp32" else 1
-    t_g = timeit(lambda: lib.gps_linear_forward(b.x.data_ptr(), d, W.data_ptr(), d, bias.data_ptr(), Y.data_ptr(), Wy,
-                                                N, Wy, d, -1, prec, stream))
+    gY = torch.randn(N, Wy, device=dev)
+    gx = torch.zeros(N, d, device=dev)
+    # split-K 4 accumulates atomically into gx (the layer zeroes it with a memset that is not part of the kernel)
+    t_g = timeit(lambda: lib.gps_gemm(gY.data_ptr(), Wy, 0, W.data_ptr(), d, 1, gx.data_ptr(), d, N, d, Wy, 4, prec, 0,
+                                      stream))
     flops = 2.0 * N * Wy * d
     res["gemm"] = {"bound": "tensor", "achieved": flops / t_g / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
-                   "frac": flops / t_g / 1e12 / pk["tensor"], "traffic": None, "seconds": t_g,
-                   "kernel": "node projection GEMM [N,7d]=[N,d]x[7d,d]^T", "peak_source": pk["source"]}
-    # (2) GatedGCN gather-reduce: algorithmic bytes s*(5N+2E)*d
+                   "frac": flops / t_g / 1e12 / pk["tensor"], "traffic": traffic.get("gemm_dgrad_x"), "seconds": t_g,
+                   "kernel": "k_gemm_tc data gradient g_x[N,d] = gY1[N,7d] x Wcat[7d,d] (tcgen05, split-bf16 x3, split-K 4)",
+                   "algorithmic_flops": flops, "peak_source": pk["source"]}
+    Y = torch.randn(N, Wy, device=dev)
     Ce = torch.randn(E, d, device=dev)
     xt = torch.empty(N, d, device=dev)
     sx = torch.zeros(2, d, device=dev, dtype=torch.float64)
@@ -511,8 +567,9 @@ def roofline_probe(lib, layer, b, spec, heads, args):
                                                             stream))
     nbytes = 4.0 * (5 * N + 2 * E) * d
     res["scatter"] = {"bound": "hbm", "achieved": nbytes / t_s / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                      "frac": nbytes / t_s / 1e9 / pk["hbm"], "traffic": None, "seconds": t_s,
-                      "kernel": "GatedGCN CSR segmented gather-reduce (fwd)", "peak_source": pk["source"]}
+                      "frac": nbytes / t_s / 1e9 / pk["hbm"], "traffic": traffic.get("gatedgcn_fwd"), "seconds": t_s,
+                      "kernel": "k_gatedgcn_fwd CSR segmented gather-reduce (+BatchNorm column sums)",
+                      "algorithmic_bytes": nbytes, "peak_source": pk["source"]}
     dom = "gemm" if t_g >= t_s else "scatter"
     out = dict(res[dom])
     out["other"] = res["scatter" if dom == "gemm" else "gemm"]
