@@ -29,7 +29,17 @@ struct GemmParams {
   int splitk = 1;
   float* colsum_a = nullptr;               // ta==1 only: += sum_k Aop[m,k]  (bias gradient), [M]
   int precision = GPS_PREC_FP32;
+  // optional pre-packed image of B (tb == 0 only; see prepack_weights): bf16 hi plane at bpk, lo plane at
+  // bpk + bpk_lo_off, bpk_groups 8-row groups per 64-wide k-block, this GEMM's B starts at packed row bpk_row0
+  const void* bpk = nullptr; int64_t bpk_lo_off = 0; int bpk_groups = 0; int bpk_row0 = 0;
 };
+
+// Pre-packs up to 8 weight matrices (fp32 [rows, K] row-major) into the tcgen05 kernel's shared-memory tile image.
+struct PrepackItem { const float* W; int rows; int K; int ld; void* dst; };   // dst sized by prepack_bytes()
+int64_t prepack_bytes(int rows, int K);          // both planes
+int64_t prepack_plane_bytes(int rows, int K);    // offset of the lo plane
+int prepack_groups(int rows);
+int prepack_weights(const PrepackItem* items, int n, cudaStream_t stream);
 
 // exact fp32 CUDA-core product (validation path and shapes the tensor-core kernel does not take)
 int gemm_simt(const GemmParams& p, cudaStream_t stream);

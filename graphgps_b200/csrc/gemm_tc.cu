@@ -65,6 +65,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (++spins > kSpinLimit) __trap();  // never hang the GPU: a protocol bug becomes an error
   }
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// 1-D bulk TMA: global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -181,13 +190,21 @@ struct TcArgs {
   int stages;
   int kb_per_split;
   int tmem_cols;
+  const uint8_t* bpk_hi;   // pre-packed K-major B planes (BPRE variants), else null
+  const uint8_t* bpk_lo;
+  int bpk_groups;          // 8-row groups per k-block in the packed planes
+  int bpk_row0;            // first row of this GEMM's B inside the packed matrix (multiple of 8)
   int debug;       // perf-triage switches (gps_debug_set): 1 no global loads, 2 no convert/store, 4 no MMA, 8 no epilogue
 };
 
 // NBC = B chunks per producer thread per k-block (2: tiles up to 64 columns, 8: up to 256).  The narrow variant
 // fits in 112 registers and ~100 KB of shared memory, so two CTAs share an SM and one CTA's load/convert phase
 // overlaps the other's MMA/epilogue phase.
-template <bool A_MN, bool B_MN, bool SPLIT, int NBC>
+// BPRE: the B operand (an nn.Linear weight, K-major) was pre-packed once per step by k_prepack_weights into
+// bf16 hi/lo planes that already have the shared-memory image of a tile (SWIZZLE_128B rows, 8-row groups, one
+// 64-wide k-block after the other), so a stage's B tile is ONE contiguous range: a single elected thread fetches
+// it with bulk TMA (cp.async.bulk ... mbarrier::complete_tx) and the producer warps only stage A.
+template <bool A_MN, bool B_MN, bool SPLIT, int NBC, bool BPRE>
 __global__ void __launch_bounds__(kThreads, NBC == 2 ? 2 : 1) k_gemm_tc(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const GemmParams& p = a.p;
@@ -210,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, NBC == 2 ? 2 : 1) k_gemm_tc(const Tc
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(smem_u32(&bars[s]), kProducerWarps);
+      mbar_init(smem_u32(&bars[s]), kProducerWarps + (BPRE ? 1 : 0));
       mbar_init(smem_u32(&bars[S + s]), 1);
     }
     mbar_init(smem_u32(&bars[2 * S]), 1);
@@ -303,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, NBC == 2 ? 2 : 1) k_gemm_tc(const Tc
         va[q][1] = ok ? ld4(src + 4) : f4zero();
       }
 #pragma unroll
-      for (int q = 0; q < NBC; ++q) {
+      for (int q = 0; q < (BPRE ? 0 : NBC); ++q) {
         const bool ok = !(a.debug & 1) && q < nb_chunks &&
                         (B_MN ? (b_row0 < p.N && b_k0 + q * (kProducerThreads >> b_rcs) < krem)
                               : (b_row0 + 32 * q < p.N && b_k0 < krem));
@@ -326,6 +343,13 @@ __global__ void __launch_bounds__(kThreads, NBC == 2 ? 2 : 1) k_gemm_tc(const Tc
       uint8_t* sa_lo = st + kATileBytes;
       uint8_t* sb_hi = st + plane * kATileBytes;
       uint8_t* sb_lo = sb_hi + b_tile_bytes;
+      if (BPRE && tid == 0) {   // bulk TMA of the pre-packed weight tile(s) of this k-block
+        const int64_t off = ((int64_t)(kb_begin + i) * a.bpk_groups + ((n0 + a.bpk_row0) >> 3)) * 1024;
+        const uint32_t bar = smem_u32(&bars[s]);
+        mbar_arrive_expect_tx(bar, (uint32_t)(plane * b_tile_bytes));
+        tma_bulk_g2s(smem_u32(sb_hi), a.bpk_hi + off, (uint32_t)b_tile_bytes, bar);
+        if (SPLIT) tma_bulk_g2s(smem_u32(sb_lo), a.bpk_lo + off, (uint32_t)b_tile_bytes, bar);
+      }
       if (!(a.debug & 2)) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -335,14 +359,14 @@ __global__ void __launch_bounds__(kThreads, NBC == 2 ? 2 : 1) k_gemm_tc(const Tc
           if (SPLIT) *reinterpret_cast<uint4*>(sa_lo + a_s0 + q * a_sq) = lo;
         }
 #pragma unroll
-        for (int q = 0; q < NBC; ++q)
+        for (int q = 0; q < (BPRE ? 0 : NBC); ++q)
           if (q < nb_chunks) {
             uint4 hi, lo;
             split8(reinterpret_cast<const float*>(vb[q]), hi, lo);
             *reinterpret_cast<uint4*>(sb_hi + b_s0 + q * b_sq) = hi;
             if (SPLIT) *reinterpret_cast<uint4*>(sb_lo + b_s0 + q * b_sq) = lo;
           }
-      } else if (va[0][0].x == 123.456f) { sa_hi[0] = (uint8_t)vb[0][0].x; }   // keep the loads alive
+      } else if (va[0][0].x == 123.456f) { sa_hi[0] = (uint8_t)va[1][0].x; }   // keep the loads alive
       fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars[s]));
@@ -493,21 +517,27 @@ int g_tc_force_bn = 0;
 
 inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
-template <bool A_MN, bool B_MN, bool SPLIT, int NBC>
+template <bool A_MN, bool B_MN, bool SPLIT, int NBC, bool BPRE>
 int launch1(const TcArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    GPS_CUDA(cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN, SPLIT, NBC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    GPS_CUDA(cudaFuncSetAttribute(k_gemm_tc<A_MN, B_MN, SPLIT, NBC, BPRE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024));
     attr_done = true;
   }
-  k_gemm_tc<A_MN, B_MN, SPLIT, NBC><<<grid, kThreads, smem, stream>>>(a);
+  k_gemm_tc<A_MN, B_MN, SPLIT, NBC, BPRE><<<grid, kThreads, smem, stream>>>(a);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }
 template <bool A_MN, bool B_MN, bool SPLIT>
 int launch(const TcArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
-  return a.nb_blocks == 1 ? launch1<A_MN, B_MN, SPLIT, 2>(a, grid, smem, stream)
-                          : launch1<A_MN, B_MN, SPLIT, 8>(a, grid, smem, stream);
+  if constexpr (!A_MN && !B_MN) {
+    if (a.bpk_hi)
+      return a.nb_blocks == 1 ? launch1<false, false, SPLIT, 2, true>(a, grid, smem, stream)
+                              : launch1<false, false, SPLIT, 8, true>(a, grid, smem, stream);
+  }
+  return a.nb_blocks == 1 ? launch1<A_MN, B_MN, SPLIT, 2, false>(a, grid, smem, stream)
+                          : launch1<A_MN, B_MN, SPLIT, 8, false>(a, grid, smem, stream);
 }
 
 }  // namespace
@@ -582,6 +612,13 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
   a.p.splitk = p.splitk > 1 ? 2 : 1;   // "accumulate atomically" flag
   a.tmem_cols = a.BN <= 32 ? 32 : a.BN <= 64 ? 64 : a.BN <= 128 ? 128 : 256;
   a.debug = g_tc_debug;
+  a.bpk_hi = a.bpk_lo = nullptr; a.bpk_groups = 0; a.bpk_row0 = 0;
+  if (p.bpk && !p.ta && !p.tb && p.bpk_row0 % 8 == 0 && (split ? p.bpk_lo_off > 0 : true)) {
+    a.bpk_hi = (const uint8_t*)p.bpk;
+    a.bpk_lo = a.bpk_hi + p.bpk_lo_off;
+    a.bpk_groups = p.bpk_groups;
+    a.bpk_row0 = p.bpk_row0;
+  }
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 1) * 8 + 16 + 16 * 16 * 8 * 4;
   dim3 grid((unsigned)ceil_div(p.N, a.BN), (unsigned)mt, (unsigned)splitk);
   const bool amn = p.ta != 0, bmn = p.tb != 0;
@@ -596,4 +633,52 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
   return GPS_ERR_UNSUPPORTED;
 }
 
+}  // namespace gps
+
+// ------------------------------------------------------------------------------------ weight pre-packing
+namespace gps {
+namespace {
+struct PrepackDesc {
+  PrepackItem it[8];
+  int n;
+};
+// one CTA per (item, k-block, 8-row group): writes the 1024-byte swizzled group of the hi and lo planes
+__global__ void k_prepack_weights(PrepackDesc d) {
+  const PrepackItem& it = d.it[blockIdx.z];
+  const int nkb = (it.K + 63) / 64, groups = (it.rows + 256 + 7) / 8;
+  const int kb = blockIdx.y, grp = blockIdx.x;
+  if (kb >= nkb || grp >= groups) return;
+  const int r = threadIdx.x >> 3, ck = threadIdx.x & 7;      // 64 threads: 8 rows x 8 sixteen-byte chunks
+  const int row = grp * 8 + r, k = kb * 64 + ck * 8;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = (row < it.rows && k + i < it.K) ? it.W[(int64_t)row * it.ld + k + i] : 0.f;
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  const int64_t plane = (int64_t)nkb * groups * 1024;
+  uint8_t* base = reinterpret_cast<uint8_t*>(it.dst) + ((int64_t)kb * groups + grp) * 1024 + r * 128 + ((ck ^ r) << 4);
+  *reinterpret_cast<uint4*>(base) = hi;
+  *reinterpret_cast<uint4*>(base + plane) = lo;
+}
+}  // namespace
+
+int prepack_groups(int rows) { return (rows + 256 + 7) / 8; }
+int64_t prepack_plane_bytes(int rows, int K) { return (int64_t)((K + 63) / 64) * prepack_groups(rows) * 1024; }
+int64_t prepack_bytes(int rows, int K) { return 2 * prepack_plane_bytes(rows, K); }
+
+int prepack_weights(const PrepackItem* items, int n, cudaStream_t stream) {
+  if (n <= 0) return GPS_OK;
+  GPS_REQUIRE(n <= 8, GPS_ERR_ARG, "prepack_weights: at most 8 matrices per call");
+  PrepackDesc d;
+  d.n = n;
+  int max_groups = 0, max_kb = 0;
+  for (int i = 0; i < n; ++i) {
+    d.it[i] = items[i];
+    max_groups = std::max(max_groups, prepack_groups(items[i].rows));
+    max_kb = std::max(max_kb, (items[i].K + 63) / 64);
+  }
+  k_prepack_weights<<<dim3((unsigned)max_groups, (unsigned)max_kb, (unsigned)n), 64, 0, stream>>>(d);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
 }  // namespace gps

@@ -158,6 +158,9 @@ struct Plan {
   // saved
   float *Wcat, *bcat, *Y1, *ehat, *xt, *xloc, *O, *lse, *hA, *s, *hid, *hid_pre, *t, *bnbuf;
   float *agg, *h1, *h1_pre;
+  // pre-packed bf16 hi/lo weight planes for the forward GEMMs (bulk-TMA B operand)
+  uint8_t *pk_cat, *pk_C, *pk_out, *pk_ff1, *pk_ff2, *pk_g0, *pk_g1;
+  bool prepack;
   int64_t saved_bytes;
   // forward workspace
   double* fstats;
@@ -253,6 +256,19 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
   P->hid = S.alloc<float>(N * 2 * d);
   if (gelu) P->hid_pre = S.alloc<float>(N * 2 * d);
   P->t = S.alloc<float>(N * d);
+  P->prepack = (d % 8 == 0) && (!P->perf || P->inner % 8 == 0);
+  if (P->prepack) {
+    const int64_t kout = P->perf ? P->inner : d;
+    if (P->Wy) P->pk_cat = S.alloc<uint8_t>(prepack_bytes((int)P->Wy, (int)d));
+    if (P->gated) P->pk_C = S.alloc<uint8_t>(prepack_bytes((int)d, (int)d));
+    if (P->attn || P->perf) P->pk_out = S.alloc<uint8_t>(prepack_bytes((int)d, (int)kout));
+    P->pk_ff1 = S.alloc<uint8_t>(prepack_bytes((int)(2 * d), (int)d));
+    P->pk_ff2 = S.alloc<uint8_t>(prepack_bytes((int)d, (int)(2 * d)));
+    if (P->gine) {
+      P->pk_g0 = S.alloc<uint8_t>(prepack_bytes((int)d, (int)d));
+      P->pk_g1 = S.alloc<uint8_t>(prepack_bytes((int)d, (int)d));
+    }
+  }
   P->saved_bytes = S.used;
   GPS_REQUIRE(!S.overflow, GPS_ERR_ARG, "saved buffer too small (%lld < %lld)", (long long)a->saved_bytes,
               (long long)S.used);
@@ -475,6 +491,36 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
   cudaStream_t s2 = sd ? sd->s : st;
   const bool two_branches = (P.gated || P.gine) && (P.attn || P.perf);
 
+  // weights: concatenate the node projections, then pre-pack every forward weight into the tcgen05 kernel's
+  // shared-memory tile image (bf16 hi/lo planes) so its B operand arrives by bulk TMA
+  if (P.Wy) {
+    PackDesc pdsc0 = pack_desc(a, P);
+    k_pack<<<(unsigned)pdsc0.total_rows, 128, 0, st>>>(pdsc0, P.Wcat, P.bcat);
+    GPS_LAUNCH_CHECK();
+  }
+  auto set_bpk = [&](GemmParams& g, const uint8_t* pk, int64_t rows, int64_t K, int64_t row0) {
+    if (!P.prepack || !pk) return;
+    g.bpk = pk;
+    g.bpk_lo_off = prepack_plane_bytes((int)rows, (int)K);
+    g.bpk_groups = prepack_groups((int)rows);
+    g.bpk_row0 = (int)row0;
+  };
+  if (P.prepack) {
+    PrepackItem items[8];
+    int ni = 0;
+    const int64_t kout = P.perf ? P.inner : d;
+    if (P.Wy) items[ni++] = PrepackItem{P.Wcat, (int)P.Wy, (int)d, (int)d, P.pk_cat};
+    if (P.gated) items[ni++] = PrepackItem{a->gcn_C.weight, (int)d, (int)d, (int)d, P.pk_C};
+    if (P.attn || P.perf) items[ni++] = PrepackItem{a->attn_out.weight, (int)d, (int)kout, (int)kout, P.pk_out};
+    items[ni++] = PrepackItem{a->ff1.weight, (int)(2 * d), (int)d, (int)d, P.pk_ff1};
+    items[ni++] = PrepackItem{a->ff2.weight, (int)d, (int)(2 * d), (int)(2 * d), P.pk_ff2};
+    if (P.gine) {
+      items[ni++] = PrepackItem{a->gine_lin0.weight, (int)d, (int)d, (int)d, P.pk_g0};
+      items[ni++] = PrepackItem{a->gine_lin1.weight, (int)d, (int)d, (int)d, P.pk_g1};
+    }
+    GPS_TRY(prepack_weights(items, ni, st));
+  }
+
   if (P.gated) {   // edge projection has no dependency on the node side: run it next to the node projections
     GPS_REQUIRE(a->edge_out, GPS_ERR_ARG, "edge_out is null");
     if (sd) GPS_TRY(sd->fork(st));
@@ -482,15 +528,11 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.M = (int)E; g.N = (int)d; g.K = (int)d;
     g.A = a->edge_attr; g.lda = (int)d; g.B = a->gcn_C.weight; g.ldb = (int)d; g.C = P.ehat; g.ldc = (int)d;
     g.bias = a->gcn_C.bias; g.precision = a->precision;
+    set_bpk(g, P.pk_C, d, d, 0);
     GPS_TRY(gemm(g, s2));
   }
 
   // ---- node projections: [Ax|Bx|Dx|Ex|Q|K|V] = x Wcat^T + bcat  (gatedgcn_layer.py:57-61, MHA in_proj)
-  if (P.Wy) {
-    PackDesc pdsc = pack_desc(a, P);
-    k_pack<<<(unsigned)pdsc.total_rows, 128, 0, st>>>(pdsc, P.Wcat, P.bcat);
-    GPS_LAUNCH_CHECK();
-  }
   // The two consumers of the projections get their own GEMM: [Ax|Bx|Dx|Ex] on the main stream for the
   // message-passing branch, [Q|K|V] on the attention branch's stream, so both branches start ~25 us after the
   // pack instead of after one 50 us GEMM.
@@ -506,6 +548,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
       g.M = (int)N; g.N = (int)wg; g.K = (int)d;
       g.A = a->x; g.lda = (int)d; g.B = P.Wcat + wl * d; g.ldb = (int)d; g.C = P.Y1 + wl; g.ldc = (int)P.Wy;
       g.bias = P.bcat + wl; g.precision = a->precision;
+      set_bpk(g, P.pk_cat, P.Wy, d, wl);
       GPS_TRY(gemm(g, sg));
     }
     if (wl > 0) {
@@ -513,6 +556,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
       g.M = (int)N; g.N = (int)wl; g.K = (int)d;
       g.A = a->x; g.lda = (int)d; g.B = P.Wcat; g.ldb = (int)d; g.C = P.Y1; g.ldc = (int)P.Wy;
       g.bias = P.bcat; g.precision = a->precision;
+      set_bpk(g, P.pk_cat, P.Wy, d, 0);
       GPS_TRY(gemm(g, st));
     }
   }
@@ -535,6 +579,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.M = (int)N; g.N = (int)d; g.K = (int)d;
     g.A = P.agg; g.lda = (int)d; g.B = a->gine_lin0.weight; g.ldb = (int)d; g.C = P.h1; g.ldc = (int)d;
     g.bias = a->gine_lin0.bias; g.act = act; g.C_pre = P.h1_pre; g.ldpre = (int)d; g.precision = a->precision;
+    set_bpk(g, P.pk_g0, d, d, 0);
     GPS_TRY(gemm(g, st));
     GemmParams g2;  // x_loc = x + drop(h1 W1^T + b1)  (gps_layer.py:188-189)
     g2.M = (int)N; g2.N = (int)d; g2.K = (int)d;
@@ -543,6 +588,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g2.p_drop = pd; g2.seed = a->seed; g2.offset = a->offset; g2.site = GPS_SITE_LOCAL;
     g2.offset_dev = (const unsigned long long*)a->offset_dev;
     g2.precision = a->precision;
+    set_bpk(g2, P.pk_g1, d, d, 0);
     GPS_TRY(gemm(g2, st));
   }
 
@@ -558,6 +604,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.p_drop = pd; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_ATTN_OUT;
     g.offset_dev = (const unsigned long long*)a->offset_dev;
     g.precision = a->precision;
+    set_bpk(g, P.pk_out, d, d, 0);
     GPS_TRY(gemm(g, sg));
   }
 
@@ -617,6 +664,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.bias = a->ff1.bias; g.act = act; g.C_pre = P.hid_pre; g.ldpre = (int)(2 * d);
     g.p_drop = pd; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_FF1; g.precision = a->precision;
     g.offset_dev = (const unsigned long long*)a->offset_dev;
+    set_bpk(g, P.pk_ff1, 2 * d, d, 0);
     GPS_TRY(gemm(g, st));
     GemmParams g2;
     g2.M = (int)N; g2.N = (int)d; g2.K = (int)(2 * d);
@@ -624,6 +672,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g2.bias = a->ff2.bias; g2.R1 = P.s; g2.ldr1 = (int)d; g2.stats = stats(BN_2);
     g2.p_drop = pd; g2.seed = a->seed; g2.offset = a->offset; g2.site = GPS_SITE_FF2; g2.precision = a->precision;
     g2.offset_dev = (const unsigned long long*)a->offset_dev;
+    set_bpk(g2, P.pk_ff2, d, 2 * d, 0);
     GPS_TRY(gemm(g2, st));
     GPS_TRY(bn_combine(P.t, bn_view_fwd(P, a, BN_2, a->norm2, N), nullptr, BnView(), a->x_out, N, d, st));  // :229
   }
