@@ -92,6 +92,7 @@ SYMBOLS = {
     "gps_dropout_mask": (C.c_int, [_fp, _i64, _i64, _f32, _u64, _u64, _i32, _fp]),
     # not in the header's stage list but part of the ABI: launch counter for bench.py
     "gps_launch_count": (C.c_ulonglong, []),
+    "gps_debug_set": (None, [C.c_int]),
 }
 
 _lib = None

@@ -263,30 +263,6 @@ struct OpAdd3 {
   __device__ void finish(int, int) {}
 };
 
-__global__ void k_bn_finalize(const double* __restrict__ sums, int64_t n, int64_t d, float* __restrict__ mean,
-                              float* __restrict__ invstd, GpsBatchNorm bn) {
-  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c == 0 && bn.num_batches_tracked) *bn.num_batches_tracked += 1;
-  if (c >= d) return;
-  double m = sums[c] / (double)n;
-  double var = sums[d + c] / (double)n - m * m;
-  if (var < 0.0) var = 0.0;
-  mean[c] = (float)m;
-  invstd[c] = (float)(1.0 / sqrt(var + (double)kBnEps));
-  if (bn.running_mean) bn.running_mean[c] = (1.f - kBnMomentum) * bn.running_mean[c] + kBnMomentum * (float)m;
-  if (bn.running_var) {
-    double unbiased = n > 1 ? var * (double)n / (double)(n - 1) : var;
-    bn.running_var[c] = (1.f - kBnMomentum) * bn.running_var[c] + kBnMomentum * (float)unbiased;
-  }
-}
-
-__global__ void k_bn_eval_prep(int64_t d, float* __restrict__ mean, float* __restrict__ invstd, GpsBatchNorm bn) {
-  int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (c >= d) return;
-  mean[c] = bn.running_mean[c];
-  invstd[c] = rsqrtf(bn.running_var[c] + kBnEps);
-}
-
 template <class Op>
 static int launch_rowwise(Op op, int64_t rows, int64_t d, cudaStream_t stream) {
   if (rows == 0) return GPS_OK;
@@ -298,20 +274,6 @@ static int launch_rowwise(Op op, int64_t rows, int64_t d, cudaStream_t stream) {
 }
 
 }  // namespace
-
-int bn_finalize(const double* sums, int64_t n, int64_t d, float* mean, float* invstd, const GpsBatchNorm& bn,
-                cudaStream_t stream) {
-  k_bn_finalize<<<(unsigned)ceil_div(d, 128), 128, 0, stream>>>(sums, n > 0 ? n : 1, d, mean, invstd, bn);
-  GPS_LAUNCH_CHECK();
-  return GPS_OK;
-}
-
-int bn_eval_prep(int64_t d, float* mean, float* invstd, const GpsBatchNorm& bn, cudaStream_t stream) {
-  GPS_REQUIRE(bn.running_mean && bn.running_var, GPS_ERR_ARG, "eval-mode BatchNorm needs running statistics");
-  k_bn_eval_prep<<<(unsigned)ceil_div(d, 128), 128, 0, stream>>>(d, mean, invstd, bn);
-  GPS_LAUNCH_CHECK();
-  return GPS_OK;
-}
 
 int bn_act_residual(const float* z, int64_t ldz, const float* R, float* out, int64_t rows, int64_t d, BnView bn,
                     int act, DropCfg drop, double* stats, cudaStream_t stream) {

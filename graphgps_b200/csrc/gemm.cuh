@@ -46,7 +46,6 @@ int gemm_simt(const GemmParams& p, cudaStream_t stream);
 // tcgen05 tensor-core product; returns GPS_ERR_UNSUPPORTED for shapes it does not take
 int gemm_tc(const GemmParams& p, cudaStream_t stream);
 void gemm_tc_set_debug(int v);
-void gemm_tc_set_trace(long long* p);
 // dispatcher used by the layer
 int gemm(const GemmParams& p, cudaStream_t stream);
 

@@ -136,38 +136,6 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// Loads chunk `c` (8 fp32 values) of a [rows x 64k] operand tile.
-//  K-major source (MN == false): element (r, k) at P[r*ld + k]; chunk c -> row c/8, k-chunk c%8.
-//  MN-major source (MN == true): element (r, k) at P[k*ld + r]; chunk c -> k-row c/(rows/8), r-chunk c%(rows/8).
-template <bool MN>
-__device__ __forceinline__ void load_chunk(const float* __restrict__ P, int64_t ld, int rows_total, int k_end, int r0,
-                                           int k0, int c, int tile_rows, float* v) {
-  int r, k;
-  if (!MN) { r = r0 + (c >> 3); k = k0 + (c & 7) * 8; }
-  else { const int rc = tile_rows >> 3; k = k0 + c / rc; r = r0 + (c % rc) * 8; }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = 0.f;
-  if (!MN) {
-    if (r >= rows_total || k >= k_end) return;
-    const float* src = P + (int64_t)r * ld + k;
-    if (k + 8 <= k_end) {
-      float4 a = ld4(src), b = ld4(src + 4);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
-      for (int i = 0; i < 8; ++i) if (k + i < k_end) v[i] = src[i];
-    }
-  } else {
-    if (k >= k_end || r >= rows_total) return;
-    const float* src = P + (int64_t)k * ld + r;
-    if (r + 8 <= rows_total) {
-      float4 a = ld4(src), b = ld4(src + 4);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    } else {
-      for (int i = 0; i < 8; ++i) if (r + i < rows_total) v[i] = src[i];
-    }
-  }
-}
-
 // Byte offset of chunk `c` inside an operand tile stored in the canonical SWIZZLE_128B layout.
 //  K-major : rows of 128 B (64 bf16 of K), 8-row groups of 1024 B.
 //  MN-major: 64-column blocks of kBBlockBytes; inside a block 8-k-row groups of 1024 B, each k-row 128 B.
@@ -546,7 +514,6 @@ void gemm_tc_set_debug(int v) {   // low 4 bits: triage switches; bits 8.. : for
   g_tc_debug = v & 0xFF;
   g_tc_force_bn = (v >> 8) & 0x1FF;
 }
-void gemm_tc_set_trace(long long*) {}
 
 int gemm_tc(const GemmParams& p, cudaStream_t stream) {
   static const int mode = [] {

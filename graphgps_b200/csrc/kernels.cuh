@@ -34,14 +34,6 @@ struct DropCfg {
   const unsigned long long* offset_dev = nullptr;  // optional device-resident addend (CUDA-graph replays)
 };
 
-// ---- BatchNorm statistics -----------------------------------------------------------------
-// training: sums [2][d] (double) over n rows -> mean/invstd (float, kept for backward) and the
-// running-stat update of torch.nn.BatchNorm1d (momentum 0.1, unbiased variance).
-int bn_finalize(const double* sums, int64_t n, int64_t d, float* mean, float* invstd, const GpsBatchNorm& bn,
-                cudaStream_t stream);
-// eval: mean = running_mean, invstd = rsqrt(running_var + eps)
-int bn_eval_prep(int64_t d, float* mean, float* invstd, const GpsBatchNorm& bn, cudaStream_t stream);
-
 // ---- forward row-wise stages ----------------------------------------------------------------
 // out = R + dropout(act(BN(z)))  [+ column sums of out into stats]   (gatedgcn_layer.py:72-83)
 int bn_act_residual(const float* z, int64_t ldz, const float* R, float* out, int64_t rows, int64_t d,

@@ -354,13 +354,6 @@ static BnView bn_view_fwd(const Plan& P, const GpsLayerArgs* a, int which, const
   return v;
 }
 
-static int bn_ready(const Plan& P, const GpsLayerArgs* a, int which, const GpsBatchNorm& bn, int64_t n,
-                    cudaStream_t st) {
-  float* mean = P.bnbuf + (int64_t)which * 2 * P.d;
-  if (a->training) return bn_finalize(P.fstats + (int64_t)which * 2 * P.d, n, P.d, mean, mean + P.d, bn, st);
-  return bn_eval_prep(P.d, mean, mean + P.d, bn, st);
-}
-
 static PackDesc pack_desc(const GpsLayerArgs* a, const Plan& P) {
   PackDesc pd;
   memset(&pd, 0, sizeof(pd));
@@ -963,7 +956,6 @@ extern "C" int gps_abi_version(void) { return GPS_ABI_VERSION; }
 extern "C" const char* gps_build_arch(void) { return "sm_100a"; }
 extern "C" unsigned long long gps_launch_count(void) { return g_launches.load(); }
 extern "C" void gps_debug_set(int v) { gemm_tc_set_debug(v); }
-extern "C" void gps_debug_trace(long long* p) { gemm_tc_set_trace(p); }  // perf-triage switches of the tcgen05 GEMM (tools/)
 
 extern "C" int gps_layer_plan(const GpsLayerArgs* args, GpsLayerPlan* plan) {
   GPS_REQUIRE(args && plan, GPS_ERR_ARG, "gps_layer_plan: null argument");

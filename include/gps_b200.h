@@ -51,6 +51,9 @@ const char* gps_build_arch(void);
 /* number of CUDA kernels this library has launched in the calling process (bench.py reports the
  * delta over its timed region as `gpu_launches`) */
 unsigned long long gps_launch_count(void);
+/* bring-up / tuning hook of the tcgen05 GEMM (tools/gemm_triage.py, tools/gemm_tune.py): low byte = stage
+ * switches (1 no global loads, 2 no convert/store, 4 no MMA, 8 no epilogue), bits 8.. = forced tile width. 0 = normal. */
+void gps_debug_set(int v);
 
 /* ------------------------------------------------------------------------------------------
  * Graph structure of one mini-batch (constant across the L layers and across fwd/bwd).

@@ -19,7 +19,7 @@ def test_shard_graph_range_partitions():
             assert max(sizes) - min(sizes) <= 1
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, outdir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.manual_seed(0)
@@ -30,22 +30,41 @@ def _worker(rank, world, port, q):
     params[2].grad = None                       # unused parameter: skipped
     bucket = allreduce_gradients(params)
     bucket2 = allreduce_gradients(params, bucket)   # bucket reuse, values already equal -> unchanged
-    q.put((rank, params[0].grad.clone(), params[1].grad.clone(), bucket2 is bucket))
+    torch.save((rank, params[0].grad.clone(), params[1].grad.clone(), bucket2 is bucket),
+               os.path.join(outdir, f"rank{rank}.pt"))
+    dist.barrier()
     dist.destroy_process_group()
 
 
-def test_bucketed_allreduce_world2():
+def _free_port():
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run_world2(outdir):
     ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, outdir)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in range(2)]
     for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    for rank, g0, g1, reused in res:
+        p.join(timeout=120)
+    ok = all(p.exitcode == 0 for p in procs)
+    for p in procs:
+        if p.is_alive():
+            p.kill()
+    return ok
+
+
+def test_bucketed_allreduce_world2(tmp_path):
+    # results travel through files (no Queue teardown races); one retry covers a port grabbed in between
+    ok = _run_world2(str(tmp_path)) or _run_world2(str(tmp_path))
+    assert ok
+    for rank in range(2):
+        r, g0, g1, reused = torch.load(os.path.join(str(tmp_path), f"rank{rank}.pt"))
+        assert r == rank
         assert torch.allclose(g0, torch.full((5, 3), 1.5))
         assert torch.allclose(g1, torch.arange(7.0) * 1.5)
         assert reused
