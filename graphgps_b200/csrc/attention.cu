@@ -96,6 +96,7 @@ struct AttnArgs {
   float* dQ; float* dK; float* dV; int64_t ldg;
   float scale; float p_drop; uint64_t seed, offset;
   const unsigned long long* offset_dev;
+  int role;   // backward: -1 both passes in one grid (blockIdx.z), 0 key-major pass, 1 query-major pass
 };
 __device__ __forceinline__ uint64_t eff_offset(const AttnArgs& a) {
   return a.offset + ((a.p_drop > 0.f && a.offset_dev) ? *a.offset_dev : 0ull);
@@ -170,9 +171,30 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_fwd(AttnArgs a) {
   }
 }
 
-// query-major backward: dQ_i and delta_i = dO_i . O_i
+// delta_i = dO_i . O_i per (row, head): 8 lanes per pair read consecutive float4 chunks (128 B per group)
+__global__ void k_attn_delta(AttnArgs a) {
+  const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  const int sub = threadIdx.x & 7;
+  const bool ok = t < (int64_t)a.N * a.H;
+  const int64_t i = ok ? t / a.H : 0;
+  const int h = ok ? (int)(t - i * a.H) : 0;
+  const float4* go = reinterpret_cast<const float4*>(a.dO + i * a.ldo + (int64_t)h * a.hd);
+  const float4* oo = reinterpret_cast<const float4*>(a.Oc + i * a.ldo + (int64_t)h * a.hd);
+  float acc = 0.f;
+  if (ok)
+    for (int c = sub; c < a.hd / 4; c += 8) {
+      const float4 x = __ldg(go + c), y = __ldg(oo + c);
+      acc += x.x * y.x + x.y * y.y + x.z * y.z + x.w * y.w;
+    }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  if (ok && sub == 0) a.delta[t] = acc;
+}
+
+// query-major backward: dQ_i (delta precomputed by k_attn_delta)
 template <int CH, int LPR>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_q(AttnArgs a) {
+__device__ __forceinline__ void attn_bwd_q_body(const AttnArgs& a) {
   constexpr int RPW = 32 / LPR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane % LPR, rloc = lane / LPR;
@@ -194,11 +216,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_q(AttnArgs a) 
   load_slice<CH, LPR>(q, a.Q + (int64_t)ir * a.ld + hoff, sub, nch, row_ok);
   load_slice<CH, LPR>(go, a.dO + (int64_t)ir * a.ldo + hoff, sub, nch, row_ok);
   {
-    float4 oo[CH];
-    load_slice<CH, LPR>(oo, a.Oc + (int64_t)ir * a.ldo + hoff, sub, nch, row_ok);
-    float dl = group_sum<LPR>(dot_slice<CH>(go, oo));
-    if (row_ok && sub == 0) a.delta[(int64_t)i * a.H + h] = dl;
-    // keep in register via q-scaling trick below
+    const float dl = row_ok ? a.deltac[(int64_t)i * a.H + h] : 0.f;
 #pragma unroll
     for (int c = 0; c < CH; ++c) gq[c] = f4zero();
     const float lse = row_ok ? a.lsec[(int64_t)i * a.H + h] : 0.f;
@@ -246,7 +264,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_q(AttnArgs a) 
 
 // key-major backward: dK_j, dV_j
 template <int CH, int LPR>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_kv(AttnArgs a) {
+__device__ __forceinline__ void attn_bwd_kv_body(const AttnArgs& a) {
   constexpr int RPW = 32 / LPR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int sub = lane % LPR, rloc = lane / LPR;
@@ -316,16 +334,23 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd_kv(AttnArgs a)
   }
 }
 
-enum { KFWD = 0, KBWDQ = 1, KBWDKV = 2 };
+// both backward passes in one grid (blockIdx.z picks the role) so they share the SMs instead of queueing
+template <int CH, int LPR>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_bwd(AttnArgs a) {
+  const int role = a.role >= 0 ? a.role : (int)blockIdx.z;
+  if (role == 0) attn_bwd_kv_body<CH, LPR>(a);
+  else attn_bwd_q_body<CH, LPR>(a);
+}
+
+enum { KFWD = 0, KBWD = 1 };
 
 template <int CH, int LPR>
 static void launch_one(int which, const AttnArgs& a, cudaStream_t stream) {
   constexpr int RPW = 32 / LPR;
-  dim3 grid((unsigned)ceil_div(a.N, (int64_t)RPW * kWarpsPerBlock), (unsigned)a.H, 1);
+  dim3 grid((unsigned)ceil_div(a.N, (int64_t)RPW * kWarpsPerBlock), (unsigned)a.H, (which == KFWD || a.role >= 0) ? 1 : 2);
   dim3 block(kWarpsPerBlock * 32);
   if (which == KFWD) k_attn_fwd<CH, LPR><<<grid, block, 0, stream>>>(a);
-  else if (which == KBWDQ) k_attn_bwd_q<CH, LPR><<<grid, block, 0, stream>>>(a);
-  else k_attn_bwd_kv<CH, LPR><<<grid, block, 0, stream>>>(a);
+  else k_attn_bwd<CH, LPR><<<grid, block, 0, stream>>>(a);
 }
 
 static int dispatch(int which, const AttnArgs& a, cudaStream_t stream) {
@@ -363,6 +388,7 @@ int attention_fwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, 
   a.gptr = g.graph_ptr; a.B = (int)g.B; a.N = (int)g.N; a.H = (int)heads; a.hd = (int)hd;
   a.Q = Q; a.K = K; a.V = V; a.ld = ld; a.O = O; a.ldo = ldo; a.lse = lse;
   a.scale = 1.f / sqrtf((float)hd); a.p_drop = p_drop; a.seed = seed; a.offset = offset;
+  a.role = -1;
   return dispatch(KFWD, a, stream);
 }
 
@@ -376,8 +402,22 @@ int attention_bwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, 
   a.Q = Q; a.K = K; a.V = V; a.ld = ld; a.Oc = O; a.dO = dO; a.ldo = ldo; a.lsec = lse;
   a.delta = delta; a.deltac = delta; a.dQ = dQ; a.dK = dK; a.dV = dV; a.ldg = ldg;
   a.scale = 1.f / sqrtf((float)hd); a.p_drop = p_drop; a.seed = seed; a.offset = offset;
-  GPS_TRY(dispatch(KBWDQ, a, stream));
-  return dispatch(KBWDKV, a, stream);
+  if (a.N == 0) return GPS_OK;
+  const int64_t nt = (int64_t)a.N * a.H * 8;
+  k_attn_delta<<<(unsigned)ceil_div(nt, (int64_t)256), 256, 0, stream>>>(a);
+  GPS_LAUNCH_CHECK();
+  static const bool merged = [] {
+    const char* e = getenv("GPS_B200_OPT");
+    return !e || (atoi(e) & 2);
+  }();
+  if (merged) {
+    a.role = -1;
+    return dispatch(KBWD, a, stream);
+  }
+  a.role = 1;
+  GPS_TRY(dispatch(KBWD, a, stream));
+  a.role = 0;
+  return dispatch(KBWD, a, stream);
 }
 
 }  // namespace gps

@@ -31,14 +31,20 @@ struct GemmParams {
   int precision = GPS_PREC_FP32;
   // optional pre-packed image of B (tb == 0 only; see prepack_weights): bf16 hi plane at bpk, lo plane at
   // bpk + bpk_lo_off, bpk_groups 8-row groups per 64-wide k-block, this GEMM's B starts at packed row bpk_row0
-  const void* bpk = nullptr; int64_t bpk_lo_off = 0; int bpk_groups = 0; int bpk_row0 = 0;
+  // bpk_mn: the image is MN-major (tb == 1: B is [K x N]; bpk_groups = 64-column blocks per k-block)
+  const void* bpk = nullptr; int64_t bpk_lo_off = 0; int bpk_groups = 0; int bpk_row0 = 0; int bpk_mn = 0;
 };
 
 // Pre-packs up to 8 weight matrices (fp32 [rows, K] row-major) into the tcgen05 kernel's shared-memory tile image.
-struct PrepackItem { const float* W; int rows; int K; int ld; void* dst; };   // dst sized by prepack_bytes()
+// K-major (mn = 0): W is [rows x K], dst sized by prepack_bytes(rows, K).
+// MN-major (mn = 1): W is [K x rows] (rows = GEMM output columns), dst sized by prepack_bytes_mn(rows, K).
+struct PrepackItem { const float* W; int rows; int K; int ld; void* dst; int mn; };
 int64_t prepack_bytes(int rows, int K);          // both planes
 int64_t prepack_plane_bytes(int rows, int K);    // offset of the lo plane
 int prepack_groups(int rows);
+int64_t prepack_bytes_mn(int cols, int K);
+int64_t prepack_plane_bytes_mn(int cols, int K);
+int prepack_groups_mn(int cols);
 int prepack_weights(const PrepackItem* items, int n, cudaStream_t stream);
 
 // exact fp32 CUDA-core product (validation path and shapes the tensor-core kernel does not take)

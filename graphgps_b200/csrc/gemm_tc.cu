@@ -162,16 +162,18 @@ struct TcArgs {
   const uint8_t* bpk_lo;
   int bpk_groups;          // 8-row groups per k-block in the packed planes
   int bpk_row0;            // first row of this GEMM's B inside the packed matrix (multiple of 8)
+  int bpk_shift;           // 3: K-major planes (1 KB per 8 rows), 6: MN-major planes (8 KB per 64 columns)
   int debug;       // perf-triage switches (gps_debug_set): 1 no global loads, 2 no convert/store, 4 no MMA, 8 no epilogue
 };
 
 // NBC = B chunks per producer thread per k-block (2: tiles up to 64 columns, 8: up to 256).  The narrow variant
 // fits in 112 registers and ~100 KB of shared memory, so two CTAs share an SM and one CTA's load/convert phase
 // overlaps the other's MMA/epilogue phase.
-// BPRE: the B operand (an nn.Linear weight, K-major) was pre-packed once per step by k_prepack_weights into
-// bf16 hi/lo planes that already have the shared-memory image of a tile (SWIZZLE_128B rows, 8-row groups, one
-// 64-wide k-block after the other), so a stage's B tile is ONE contiguous range: a single elected thread fetches
-// it with bulk TMA (cp.async.bulk ... mbarrier::complete_tx) and the producer warps only stage A.
+// BPRE: the B operand (an nn.Linear weight) was pre-packed once per step by k_prepack_weights into bf16 hi/lo
+// planes that already have the shared-memory image of a tile (SWIZZLE_128B; K-major: 8-row groups, MN-major:
+// 64-column blocks; one 64-deep k-block after the other), so a stage's B tile is ONE contiguous range: a single
+// elected thread fetches it with bulk TMA (cp.async.bulk ... mbarrier::complete_tx) and the producer warps only
+// stage A.  K-major planes serve y = x W^T (forward), MN-major planes serve g_x = g_y W (data gradients).
 template <bool A_MN, bool B_MN, bool SPLIT, int NBC, bool BPRE>
 __global__ void __launch_bounds__(kThreads, NBC == 2 ? 2 : 1) k_gemm_tc(const TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -312,7 +314,8 @@ __global__ void __launch_bounds__(kThreads, NBC == 2 ? 2 : 1) k_gemm_tc(const Tc
       uint8_t* sb_hi = st + plane * kATileBytes;
       uint8_t* sb_lo = sb_hi + b_tile_bytes;
       if (BPRE && tid == 0) {   // bulk TMA of the pre-packed weight tile(s) of this k-block
-        const int64_t off = ((int64_t)(kb_begin + i) * a.bpk_groups + ((n0 + a.bpk_row0) >> 3)) * 1024;
+        const int64_t off = ((int64_t)(kb_begin + i) * a.bpk_groups + ((n0 + a.bpk_row0) >> a.bpk_shift))
+                            << (7 + a.bpk_shift);
         const uint32_t bar = smem_u32(&bars[s]);
         mbar_arrive_expect_tx(bar, (uint32_t)(plane * b_tile_bytes));
         tma_bulk_g2s(smem_u32(sb_hi), a.bpk_hi + off, (uint32_t)b_tile_bytes, bar);
@@ -499,10 +502,10 @@ int launch1(const TcArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
 }
 template <bool A_MN, bool B_MN, bool SPLIT>
 int launch(const TcArgs& a, dim3 grid, size_t smem, cudaStream_t stream) {
-  if constexpr (!A_MN && !B_MN) {
+  if constexpr (!A_MN) {
     if (a.bpk_hi)
-      return a.nb_blocks == 1 ? launch1<false, false, SPLIT, 2, true>(a, grid, smem, stream)
-                              : launch1<false, false, SPLIT, 8, true>(a, grid, smem, stream);
+      return a.nb_blocks == 1 ? launch1<false, B_MN, SPLIT, 2, true>(a, grid, smem, stream)
+                              : launch1<false, B_MN, SPLIT, 8, true>(a, grid, smem, stream);
   }
   return a.nb_blocks == 1 ? launch1<A_MN, B_MN, SPLIT, 2, false>(a, grid, smem, stream)
                           : launch1<A_MN, B_MN, SPLIT, 8, false>(a, grid, smem, stream);
@@ -550,10 +553,12 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
 
   // tile width: BN in {64,128,256}-block granularity (1, 2 or 4 staged 64-column blocks); the kernel is bound
   // by operand traffic ~ tiles x (128 + staged B rows), so minimise waves x staged rows, wider on ties
+  const bool pre_k = p.bpk && !p.bpk_mn && !p.ta && !p.tb && p.bpk_row0 % 8 == 0 && (split ? p.bpk_lo_off > 0 : true);
+  const bool pre_mn = p.bpk && p.bpk_mn && !p.ta && p.tb && p.bpk_row0 % 64 == 0 && (split ? p.bpk_lo_off > 0 : true);
   int bestBN = 128;
   long bestCost = -1;
   for (int nt = (int)ceil_div(p.N, 256); nt <= (int)ceil_div(p.N, 48) + 1; ++nt) {
-    int bn = (int)round_up(ceil_div(p.N, nt), 16);
+    int bn = (int)round_up(ceil_div(p.N, nt), pre_mn ? 64 : 16);   // MN-major planes are cut at 64-column blocks
     if (bn > 256) continue;
     if (bn < 16) bn = 16;
     int nb = bn <= 64 ? 1 : bn <= 128 ? 2 : 4;
@@ -562,7 +567,7 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
     long cost = waves * (BM + nb * 64L);
     if (bestCost < 0 || cost < bestCost) { bestCost = cost; bestBN = bn; }
   }
-  if (g_tc_force_bn > 0) bestBN = g_tc_force_bn;   // tuning hook (tools/gemm_tune.py)
+  if (g_tc_force_bn > 0 && !(pre_mn && g_tc_force_bn % 64)) bestBN = g_tc_force_bn;   // tuning hook (tools/gemm_tune.py)
   TcArgs a;
   a.p = p;
   a.BN = bestBN;
@@ -579,12 +584,13 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
   a.p.splitk = p.splitk > 1 ? 2 : 1;   // "accumulate atomically" flag
   a.tmem_cols = a.BN <= 32 ? 32 : a.BN <= 64 ? 64 : a.BN <= 128 ? 128 : 256;
   a.debug = g_tc_debug;
-  a.bpk_hi = a.bpk_lo = nullptr; a.bpk_groups = 0; a.bpk_row0 = 0;
-  if (p.bpk && !p.ta && !p.tb && p.bpk_row0 % 8 == 0 && (split ? p.bpk_lo_off > 0 : true)) {
+  a.bpk_hi = a.bpk_lo = nullptr; a.bpk_groups = 0; a.bpk_row0 = 0; a.bpk_shift = 3;
+  if (pre_k || pre_mn) {
     a.bpk_hi = (const uint8_t*)p.bpk;
     a.bpk_lo = a.bpk_hi + p.bpk_lo_off;
     a.bpk_groups = p.bpk_groups;
     a.bpk_row0 = p.bpk_row0;
+    a.bpk_shift = pre_mn ? 6 : 3;
   }
   const size_t smem = (size_t)stages * stage_bytes + 1024 /*align*/ + (2 * stages + 1) * 8 + 16 + 16 * 16 * 8 * 4;
   dim3 grid((unsigned)ceil_div(p.N, a.BN), (unsigned)mt, (unsigned)splitk);
@@ -606,45 +612,83 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
 namespace gps {
 namespace {
 struct PrepackDesc {
-  PrepackItem it[8];
+  PrepackItem it[16];
+  int start[17];   // CTA index range of each item (1-D grid: no empty CTAs)
   int n;
 };
-// one CTA per (item, k-block, 8-row group): writes the 1024-byte swizzled group of the hi and lo planes
+// K-major item: one CTA per (k-block, 8-row group) writes the 1024-byte swizzled group of both planes.
+// MN-major item (W is [K x cols]): one CTA per (k-block, 64-column block x 8-k-row group).
 __global__ void k_prepack_weights(PrepackDesc d) {
-  const PrepackItem& it = d.it[blockIdx.z];
-  const int nkb = (it.K + 63) / 64, groups = (it.rows + 256 + 7) / 8;
-  const int kb = blockIdx.y, grp = blockIdx.x;
-  if (kb >= nkb || grp >= groups) return;
+  int item = 0;
+  while (item + 1 < d.n && (int)blockIdx.x >= d.start[item + 1]) ++item;
+  const PrepackItem& it = d.it[item];
+  const int local = (int)blockIdx.x - d.start[item];
   const int r = threadIdx.x >> 3, ck = threadIdx.x & 7;      // 64 threads: 8 rows x 8 sixteen-byte chunks
-  const int row = grp * 8 + r, k = kb * 64 + ck * 8;
+  const int nkb = (it.K + 63) / 64;
   float v[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = (row < it.rows && k + i < it.K) ? it.W[(int64_t)row * it.ld + k + i] : 0.f;
   uint4 hi, lo;
-  split8(v, hi, lo);
-  const int64_t plane = (int64_t)nkb * groups * 1024;
-  uint8_t* base = reinterpret_cast<uint8_t*>(it.dst) + ((int64_t)kb * groups + grp) * 1024 + r * 128 + ((ck ^ r) << 4);
-  *reinterpret_cast<uint4*>(base) = hi;
-  *reinterpret_cast<uint4*>(base + plane) = lo;
+  if (!it.mn) {
+    const int groups = (it.rows + 256 + 7) / 8;
+    const int kb = local / groups, grp = local - kb * groups;
+    const int row = grp * 8 + r, k = kb * 64 + ck * 8;
+    if (row < it.rows && k + 8 <= it.K) {
+      const float4 x = ld4(it.W + (int64_t)row * it.ld + k), y = ld4(it.W + (int64_t)row * it.ld + k + 4);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (row < it.rows && k + i < it.K) ? it.W[(int64_t)row * it.ld + k + i] : 0.f;
+    }
+    split8(v, hi, lo);
+    const int64_t plane = (int64_t)nkb * groups * 1024;
+    uint8_t* base = reinterpret_cast<uint8_t*>(it.dst) + ((int64_t)kb * groups + grp) * 1024 + r * 128 + ((ck ^ r) << 4);
+    *reinterpret_cast<uint4*>(base) = hi;
+    *reinterpret_cast<uint4*>(base + plane) = lo;
+  } else {
+    // it.K = reduction extent (rows of W), it.rows = output columns of the GEMM (columns of W)
+    const int cblocks = (it.rows + 256 + 63) / 64, nx = cblocks * 8;
+    const int kb = local / nx, x = local - kb * nx;
+    const int cb = x >> 3, kg = x & 7;
+    const int k = kb * 64 + kg * 8 + r, col = cb * 64 + ck * 8;
+    if (k < it.K && col + 8 <= it.rows) {
+      const float4 x0 = ld4(it.W + (int64_t)k * it.ld + col), y0 = ld4(it.W + (int64_t)k * it.ld + col + 4);
+      v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = y0.x; v[5] = y0.y; v[6] = y0.z; v[7] = y0.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (k < it.K && col + i < it.rows) ? it.W[(int64_t)k * it.ld + col + i] : 0.f;
+    }
+    split8(v, hi, lo);
+    const int64_t plane = (int64_t)nkb * cblocks * 8192;
+    uint8_t* base = reinterpret_cast<uint8_t*>(it.dst) + ((int64_t)kb * cblocks + cb) * 8192 + kg * 1024 + r * 128 +
+                    ((ck ^ r) << 4);
+    *reinterpret_cast<uint4*>(base) = hi;
+    *reinterpret_cast<uint4*>(base + plane) = lo;
+  }
 }
 }  // namespace
 
 int prepack_groups(int rows) { return (rows + 256 + 7) / 8; }
 int64_t prepack_plane_bytes(int rows, int K) { return (int64_t)((K + 63) / 64) * prepack_groups(rows) * 1024; }
 int64_t prepack_bytes(int rows, int K) { return 2 * prepack_plane_bytes(rows, K); }
+int prepack_groups_mn(int cols) { return (cols + 256 + 63) / 64; }
+int64_t prepack_plane_bytes_mn(int cols, int K) { return (int64_t)((K + 63) / 64) * prepack_groups_mn(cols) * 8192; }
+int64_t prepack_bytes_mn(int cols, int K) { return 2 * prepack_plane_bytes_mn(cols, K); }
 
 int prepack_weights(const PrepackItem* items, int n, cudaStream_t stream) {
   if (n <= 0) return GPS_OK;
-  GPS_REQUIRE(n <= 8, GPS_ERR_ARG, "prepack_weights: at most 8 matrices per call");
+  GPS_REQUIRE(n <= 16, GPS_ERR_ARG, "prepack_weights: at most 16 matrices per call");
   PrepackDesc d;
   d.n = n;
-  int max_groups = 0, max_kb = 0;
+  int total = 0;
   for (int i = 0; i < n; ++i) {
     d.it[i] = items[i];
-    max_groups = std::max(max_groups, prepack_groups(items[i].rows));
-    max_kb = std::max(max_kb, (items[i].K + 63) / 64);
+    GPS_REQUIRE(items[i].ld % 4 == 0 && (reinterpret_cast<uintptr_t>(items[i].W) & 15) == 0, GPS_ERR_ARG,
+                "prepack_weights: weights must be 16-byte aligned with ld %% 4 == 0");
+    d.start[i] = total;
+    total += ((items[i].K + 63) / 64) * (items[i].mn ? prepack_groups_mn(items[i].rows) * 8 : prepack_groups(items[i].rows));
   }
-  k_prepack_weights<<<dim3((unsigned)max_groups, (unsigned)max_kb, (unsigned)n), 64, 0, stream>>>(d);
+  d.start[n] = total;
+  if (total == 0) return GPS_OK;
+  k_prepack_weights<<<(unsigned)total, 64, 0, stream>>>(d);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }

@@ -79,6 +79,7 @@ namespace {
 struct Side {
   cudaStream_t s = nullptr;    // weight gradients / edge projection / forward attention branch
   cudaStream_t s3 = nullptr;   // backward attention branch (next to the message-passing backward)
+  cudaStream_t s4 = nullptr;   // edge-side BatchNorm backward (depends on grad_edge_out only, so it starts at once)
   cudaEvent_t ev[32];
   int next = 0;
   bool ok = false;
@@ -86,6 +87,7 @@ struct Side {
     if (ok) return GPS_OK;
     GPS_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     GPS_CUDA(cudaStreamCreateWithFlags(&s3, cudaStreamNonBlocking));
+    GPS_CUDA(cudaStreamCreateWithFlags(&s4, cudaStreamNonBlocking));
     for (int i = 0; i < 32; ++i) GPS_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
     ok = true;
     return GPS_OK;
@@ -99,6 +101,15 @@ struct Side {
   int fork(cudaStream_t main) { return order(main, s); }
   int join(cudaStream_t main) { return order(s, main); }
 };
+
+// A/B switches (GPS_B200_OPT): 1 MN-major weight planes, 2 merged attention backward, 4 early edge BN backward
+static int opt_flags() {
+  static const int v = [] {
+    const char* e = getenv("GPS_B200_OPT");
+    return e ? atoi(e) : 7;
+  }();
+  return v;
+}
 
 static Side* side_stream() {
   static const bool enabled = [] {
@@ -160,6 +171,8 @@ struct Plan {
   float *agg, *h1, *h1_pre;
   // pre-packed bf16 hi/lo weight planes for the forward GEMMs (bulk-TMA B operand)
   uint8_t *pk_cat, *pk_C, *pk_out, *pk_ff1, *pk_ff2, *pk_g0, *pk_g1;
+  // the same weights as MN-major planes for the data-gradient GEMMs of the backward pass (training only)
+  uint8_t *pt_cat, *pt_C, *pt_out, *pt_ff1, *pt_ff2, *pt_g0, *pt_g1;
   bool prepack;
   int64_t saved_bytes;
   // forward workspace
@@ -267,6 +280,17 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
     if (P->gine) {
       P->pk_g0 = S.alloc<uint8_t>(prepack_bytes((int)d, (int)d));
       P->pk_g1 = S.alloc<uint8_t>(prepack_bytes((int)d, (int)d));
+    }
+    if (a->training) {   // W as [K = out features] x [N = in features]
+      if (P->Wy) P->pt_cat = S.alloc<uint8_t>(prepack_bytes_mn((int)d, (int)P->Wy));
+      if (P->gated) P->pt_C = S.alloc<uint8_t>(prepack_bytes_mn((int)d, (int)d));
+      if (P->attn || P->perf) P->pt_out = S.alloc<uint8_t>(prepack_bytes_mn((int)kout, (int)d));
+      P->pt_ff1 = S.alloc<uint8_t>(prepack_bytes_mn((int)d, (int)(2 * d)));
+      P->pt_ff2 = S.alloc<uint8_t>(prepack_bytes_mn((int)(2 * d), (int)d));
+      if (P->gine) {
+        P->pt_g0 = S.alloc<uint8_t>(prepack_bytes_mn((int)d, (int)d));
+        P->pt_g1 = S.alloc<uint8_t>(prepack_bytes_mn((int)d, (int)d));
+      }
     }
   }
   P->saved_bytes = S.used;
@@ -498,22 +522,38 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.bpk_groups = prepack_groups((int)rows);
     g.bpk_row0 = (int)row0;
   };
+  // Weight planes: the ones the first GEMMs need are packed on the caller's stream; the rest (output projection,
+  // FFN, and the MN-major images the backward pass reads) are packed next to those GEMMs on their own stream.
+  cudaStream_t sp = sd ? sd->s4 : st;
   if (P.prepack) {
-    PrepackItem items[8];
+    PrepackItem items[16];
     int ni = 0;
     const int64_t kout = P.perf ? P.inner : d;
     if (P.Wy) items[ni++] = PrepackItem{P.Wcat, (int)P.Wy, (int)d, (int)d, P.pk_cat};
     if (P.gated) items[ni++] = PrepackItem{a->gcn_C.weight, (int)d, (int)d, (int)d, P.pk_C};
-    if (P.attn || P.perf) items[ni++] = PrepackItem{a->attn_out.weight, (int)d, (int)kout, (int)kout, P.pk_out};
-    items[ni++] = PrepackItem{a->ff1.weight, (int)(2 * d), (int)d, (int)d, P.pk_ff1};
-    items[ni++] = PrepackItem{a->ff2.weight, (int)d, (int)(2 * d), (int)(2 * d), P.pk_ff2};
     if (P.gine) {
       items[ni++] = PrepackItem{a->gine_lin0.weight, (int)d, (int)d, (int)d, P.pk_g0};
       items[ni++] = PrepackItem{a->gine_lin1.weight, (int)d, (int)d, (int)d, P.pk_g1};
     }
     GPS_TRY(prepack_weights(items, ni, st));
+    ni = 0;
+    if (sp != st) GPS_TRY(sd->order(st, sp));
+    if (P.attn || P.perf) items[ni++] = PrepackItem{a->attn_out.weight, (int)d, (int)kout, (int)kout, P.pk_out};
+    items[ni++] = PrepackItem{a->ff1.weight, (int)(2 * d), (int)d, (int)d, P.pk_ff1};
+    items[ni++] = PrepackItem{a->ff2.weight, (int)d, (int)(2 * d), (int)(2 * d), P.pk_ff2};
+    if (a->training && (opt_flags() & 1)) {   // MN-major images for the backward data gradients: W is [K x N] there
+      if (P.Wy) items[ni++] = PrepackItem{P.Wcat, (int)d, (int)P.Wy, (int)d, P.pt_cat, 1};
+      if (P.gated) items[ni++] = PrepackItem{a->gcn_C.weight, (int)d, (int)d, (int)d, P.pt_C, 1};
+      if (P.attn || P.perf) items[ni++] = PrepackItem{a->attn_out.weight, (int)kout, (int)d, (int)kout, P.pt_out, 1};
+      items[ni++] = PrepackItem{a->ff1.weight, (int)d, (int)(2 * d), (int)d, P.pt_ff1, 1};
+      items[ni++] = PrepackItem{a->ff2.weight, (int)(2 * d), (int)d, (int)(2 * d), P.pt_ff2, 1};
+      if (P.gine) {
+        items[ni++] = PrepackItem{a->gine_lin0.weight, (int)d, (int)d, (int)d, P.pt_g0, 1};
+        items[ni++] = PrepackItem{a->gine_lin1.weight, (int)d, (int)d, (int)d, P.pt_g1, 1};
+      }
+    }
+    GPS_TRY(prepack_weights(items, ni, sp));
   }
-
   if (P.gated) {   // edge projection has no dependency on the node side: run it next to the node projections
     GPS_REQUIRE(a->edge_out, GPS_ERR_ARG, "edge_out is null");
     if (sd) GPS_TRY(sd->fork(st));
@@ -598,6 +638,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.offset_dev = (const unsigned long long*)a->offset_dev;
     g.precision = a->precision;
     set_bpk(g, P.pk_out, d, d, 0);
+    if (P.prepack && sp != st) GPS_TRY(sd->order(sp, sg));
     GPS_TRY(gemm(g, sg));
   }
 
@@ -651,6 +692,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
 
   // ---- FFN: t = s + drop(W2 drop(act(W1 s + b1)) + b2)   (gps_layer.py:225, 253-257)
   {
+    if (P.prepack && sp != st) GPS_TRY(sd->order(sp, st));
     GemmParams g;
     g.M = (int)N; g.N = (int)(2 * d); g.K = (int)d;
     g.A = P.s; g.lda = (int)d; g.B = a->ff1.weight; g.ldb = (int)d; g.C = P.hid; g.ldc = (int)(2 * d);
@@ -706,6 +748,35 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   auto wfork = [&](cudaStream_t from) -> int { return sd ? sd->order(from, s2) : GPS_OK; };
   const bool two_branches = (P.gated || P.gine) && (P.attn || P.perf);
   cudaStream_t sa = (two_branches && sd) ? sd->s3 : st;   // stream of the attention-branch backward
+  const int opt = opt_flags();
+  const bool early_edge = (opt & 4) != 0;
+  cudaStream_t se = (P.gated && sd && early_edge) ? sd->s4 : st;   // stream of the edge BatchNorm backward
+  // data gradients g_in = g_out W read W through the MN-major planes packed by the forward pass
+  auto set_bpt = [&](GemmParams& g, const uint8_t* pt, int64_t cols, int64_t K) {
+    if (!P.prepack || !pt || !(opt & 1)) return;
+    g.bpk = pt;
+    g.bpk_mn = 1;
+    g.bpk_lo_off = prepack_plane_bytes_mn((int)cols, (int)K);
+    g.bpk_groups = prepack_groups_mn((int)cols);
+    g.bpk_row0 = 0;
+  };
+
+  auto edge_bn_bwd = [&]() -> int {
+    // e_out = e + drop(act(BN_e(e^))) (gatedgcn_layer.py:76-83): g_e^ needs grad_edge_out alone -> off the critical path
+    if (se != st) GPS_TRY(sd->order(st, se));
+    BnView ve = bn_view(P, BN_E, a->bn_edge_e);
+    if (a->grad_edge_out && E > 0) {
+      GPS_TRY(bn_bwd_reduce(a->grad_edge_out, d, P.ehat, d, E, d, ve, act, drop(GPS_SITE_GCN_E), sums(BN_E), se));
+      GPS_TRY(bn_bwd_apply(a->grad_edge_out, d, P.ehat, d, E, d, ve, act, drop(GPS_SITE_GCN_E), sums(BN_E), P.g_e, d,
+                           a->bn_edge_e.grad_weight, a->bn_edge_e.grad_bias, se));
+    } else {
+      if (E > 0) GPS_CUDA(cudaMemsetAsync(P.g_e, 0, (size_t)(E * d) * sizeof(float), se));
+      if (a->bn_edge_e.grad_weight) GPS_CUDA(cudaMemsetAsync(a->bn_edge_e.grad_weight, 0, d * sizeof(float), se));
+      if (a->bn_edge_e.grad_bias) GPS_CUDA(cudaMemsetAsync(a->bn_edge_e.grad_bias, 0, d * sizeof(float), se));
+    }
+    return GPS_OK;
+  };
+  if (P.gated && early_edge) GPS_TRY(edge_bn_bwd());
 
   // ---- norm2 (gps_layer.py:229): g_t
   BnView v2 = bn_view(P, BN_2, a->norm2);
@@ -727,6 +798,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g.ldmask = (int)(2 * d);
     g.p_drop = pd; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_FF1; g.precision = prec;
     g.offset_dev = (const unsigned long long*)a->offset_dev;
+    set_bpt(g, P.pt_ff2, 2 * d, d);
     GPS_TRY(gemm(g, st));
     GPS_TRY(wfork(st));
     GPS_TRY(linear_wgrad(g_ff2, d, P.hid, 2 * d, N, d, 2 * d, a->ff2.grad_weight, a->ff2.grad_bias, prec, s2));
@@ -735,6 +807,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g2.M = (int)N; g2.N = (int)d; g2.K = (int)(2 * d);
     g2.A = P.g_hid; g2.lda = (int)(2 * d); g2.B = a->ff1.weight; g2.ldb = (int)d; g2.tb = 1; g2.C = P.g_s; g2.ldc = (int)d;
     g2.R1 = P.g_t; g2.ldr1 = (int)d; g2.precision = prec;
+    set_bpt(g2, P.pt_ff1, d, 2 * d);
     GPS_TRY(gemm(g2, st));
   }
 
@@ -762,6 +835,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g.M = (int)N; g.N = (int)d; g.K = (int)d;
     g.A = g_ao; g.lda = (int)d; g.B = a->attn_out.weight; g.ldb = (int)d; g.tb = 1; g.C = P.g_O; g.ldc = (int)d;
     g.precision = prec;
+    set_bpt(g, P.pt_out, d, d);
     GPS_TRY(gemm(g, sa));
     GPS_TRY(wfork(sa));
     GPS_TRY(linear_wgrad(g_ao, d, P.O, d, N, d, d, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, s2));
@@ -786,6 +860,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g.M = (int)N; g.N = (int)inner; g.K = (int)d;
     g.A = g_ao; g.lda = (int)d; g.B = a->attn_out.weight; g.ldb = (int)inner; g.tb = 1; g.C = P.g_O; g.ldc = (int)inner;
     g.precision = prec;
+    set_bpt(g, P.pt_out, inner, d);
     GPS_TRY(gemm(g, sa));
     GPS_TRY(wfork(sa));
     GPS_TRY(linear_wgrad(g_ao, d, P.O, inner, N, d, inner, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, s2));
@@ -829,16 +904,8 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(bn_bwd_reduce(P.g_xloc, d, P.xt, d, N, d, vx, act, drop(GPS_SITE_GCN_X), sums(BN_X), st));
     GPS_TRY(bn_bwd_apply(P.g_xloc, d, P.xt, d, N, d, vx, act, drop(GPS_SITE_GCN_X), sums(BN_X), P.gY1, P.Wy,
                          a->bn_node_x.grad_weight, a->bn_node_x.grad_bias, st));
-    BnView ve = bn_view(P, BN_E, a->bn_edge_e);
-    if (a->grad_edge_out && E > 0) {
-      GPS_TRY(bn_bwd_reduce(a->grad_edge_out, d, P.ehat, d, E, d, ve, act, drop(GPS_SITE_GCN_E), sums(BN_E), st));
-      GPS_TRY(bn_bwd_apply(a->grad_edge_out, d, P.ehat, d, E, d, ve, act, drop(GPS_SITE_GCN_E), sums(BN_E), P.g_e, d,
-                           a->bn_edge_e.grad_weight, a->bn_edge_e.grad_bias, st));
-    } else {
-      if (E > 0) GPS_CUDA(cudaMemsetAsync(P.g_e, 0, (size_t)(E * d) * sizeof(float), st));
-      if (a->bn_edge_e.grad_weight) GPS_CUDA(cudaMemsetAsync(a->bn_edge_e.grad_weight, 0, d * sizeof(float), st));
-      if (a->bn_edge_e.grad_bias) GPS_CUDA(cudaMemsetAsync(a->bn_edge_e.grad_bias, 0, d * sizeof(float), st));
-    }
+    if (!early_edge) GPS_TRY(edge_bn_bwd());
+    if (se != st) GPS_TRY(sd->order(se, st));
     // message/aggregate backward
     GPS_TRY(gatedgcn_bwd_dst(a->graph, d, P.gY1, P.Wy, P.ehat, P.Y1 + d, P.Wy, P.g_e, P.g_num, P.gY1 + 2 * d, st));
     GPS_TRY(gatedgcn_bwd_src(a->graph, d, P.g_e, P.ehat, P.g_num, P.gY1 + 3 * d, P.gY1 + d, P.Wy, st));
@@ -850,6 +917,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
       g.M = (int)E; g.N = (int)d; g.K = (int)d;
       g.A = P.g_e; g.lda = (int)d; g.B = a->gcn_C.weight; g.ldb = (int)d; g.tb = 1; g.C = a->grad_edge_attr; g.ldc = (int)d;
       g.R1 = a->grad_edge_out; g.ldr1 = (int)d; g.precision = prec;
+      set_bpt(g, P.pt_C, d, d);
       GPS_TRY(gemm(g, st));
     }
     g_x_local = P.g_xloc;  // residual x_in + ...
@@ -865,6 +933,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g.A = g_l1; g.lda = (int)d; g.B = a->gine_lin1.weight; g.ldb = (int)d; g.tb = 1; g.C = P.g_h1; g.ldc = (int)d;
     if (relu) { g.mask_src = P.h1; g.mask_is_post = 1; } else { g.mask_src = P.h1_pre; g.mask_act = act; }
     g.ldmask = (int)d; g.precision = prec;
+    set_bpt(g, P.pt_g1, d, d);
     GPS_TRY(gemm(g, st));
     GPS_TRY(wfork(st));
     GPS_TRY(linear_wgrad(g_l1, d, P.h1, d, N, d, d, a->gine_lin1.grad_weight, a->gine_lin1.grad_bias, prec, s2));
@@ -873,6 +942,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g2.M = (int)N; g2.N = (int)d; g2.K = (int)d;
     g2.A = P.g_h1; g2.lda = (int)d; g2.B = a->gine_lin0.weight; g2.ldb = (int)d; g2.tb = 1; g2.C = P.g_agg; g2.ldc = (int)d;
     g2.precision = prec;
+    set_bpt(g2, P.pt_g0, d, d);
     GPS_TRY(gemm(g2, st));
     GPS_REQUIRE(a->grad_edge_attr || E == 0, GPS_ERR_ARG, "grad_edge_attr is required for GINE");
     GPS_TRY(gine_bwd_dst(a->graph, d, a->x, a->edge_attr, P.g_agg, a->grad_edge_attr, st));
@@ -905,6 +975,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
       GPS_CUDA(cudaMemsetAsync(a->grad_x, 0, (size_t)(N * d) * sizeof(float), st));
       g.splitk = 4;
     }
+    set_bpt(g, P.pt_cat, d, P.Wy);
     GPS_TRY(gemm(g, st));
   } else if (g_x_local) {
     GPS_TRY(add3(g_x_local, d, P.perf ? P.g_xp : nullptr, d, nullptr, 0, a->grad_x, d, N, d, st));
