@@ -33,6 +33,7 @@ struct GemmParams {
   // bpk + bpk_lo_off, bpk_groups 8-row groups per 64-wide k-block, this GEMM's B starts at packed row bpk_row0
   // bpk_mn: the image is MN-major (tb == 1: B is [K x N]; bpk_groups = 64-column blocks per k-block)
   const void* bpk = nullptr; int64_t bpk_lo_off = 0; int bpk_groups = 0; int bpk_row0 = 0; int bpk_mn = 0;
+  int bpk_kb0 = 0;   // first 64-deep k-block of this GEMM inside the packed planes (reduction sub-range of a packed matrix)
 };
 
 // Pre-packs up to 8 weight matrices (fp32 [rows, K] row-major) into the tcgen05 kernel's shared-memory tile image.

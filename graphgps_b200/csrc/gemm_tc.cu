@@ -162,6 +162,7 @@ struct TcArgs {
   const uint8_t* bpk_lo;
   int bpk_groups;          // 8-row groups per k-block in the packed planes
   int bpk_row0;            // first row of this GEMM's B inside the packed matrix (multiple of 8)
+  int bpk_kb0;             // k-block offset of this GEMM's reduction range inside the planes
   int bpk_shift;           // 3: K-major planes (1 KB per 8 rows), 6: MN-major planes (8 KB per 64 columns)
   int debug;       // perf-triage switches (gps_debug_set): 1 no global loads, 2 no convert/store, 4 no MMA, 8 no epilogue
 };
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, NBC == 2 ? 2 : 1) k_gemm_tc(const Tc
       uint8_t* sb_hi = st + plane * kATileBytes;
       uint8_t* sb_lo = sb_hi + b_tile_bytes;
       if (BPRE && tid == 0) {   // bulk TMA of the pre-packed weight tile(s) of this k-block
-        const int64_t off = ((int64_t)(kb_begin + i) * a.bpk_groups + ((n0 + a.bpk_row0) >> a.bpk_shift))
+        const int64_t off = ((int64_t)(kb_begin + i + a.bpk_kb0) * a.bpk_groups + ((n0 + a.bpk_row0) >> a.bpk_shift))
                             << (7 + a.bpk_shift);
         const uint32_t bar = smem_u32(&bars[s]);
         mbar_arrive_expect_tx(bar, (uint32_t)(plane * b_tile_bytes));
@@ -584,7 +585,7 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
   a.p.splitk = p.splitk > 1 ? 2 : 1;   // "accumulate atomically" flag
   a.tmem_cols = a.BN <= 32 ? 32 : a.BN <= 64 ? 64 : a.BN <= 128 ? 128 : 256;
   a.debug = g_tc_debug;
-  a.bpk_hi = a.bpk_lo = nullptr; a.bpk_groups = 0; a.bpk_row0 = 0; a.bpk_shift = 3;
+  a.bpk_hi = a.bpk_lo = nullptr; a.bpk_groups = 0; a.bpk_row0 = 0; a.bpk_shift = 3; a.bpk_kb0 = p.bpk_kb0;
   if (pre_k || pre_mn) {
     a.bpk_hi = (const uint8_t*)p.bpk;
     a.bpk_lo = a.bpk_hi + p.bpk_lo_off;

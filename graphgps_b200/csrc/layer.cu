@@ -102,11 +102,12 @@ struct Side {
   int join(cudaStream_t main) { return order(s, main); }
 };
 
-// A/B switches (GPS_B200_OPT): 1 MN-major weight planes, 2 merged attention backward, 4 early edge BN backward
+// A/B switches (GPS_B200_OPT): 1 MN-major weight planes, 2 merged attention backward, 4 early edge BN backward,
+// 8 projection gradients split into the message-passing and attention column blocks
 static int opt_flags() {
   static const int v = [] {
     const char* e = getenv("GPS_B200_OPT");
-    return e ? atoi(e) : 7;
+    return e ? atoi(e) : 7;   // 8 measured slower on B200 (0.573 vs 0.552 ms/step, profiles/r1_ab_switches.txt)
   }();
   return v;
 }
@@ -750,6 +751,19 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   cudaStream_t sa = (two_branches && sd) ? sd->s3 : st;   // stream of the attention-branch backward
   const int opt = opt_flags();
   const bool early_edge = (opt & 4) != 0;
+  // [Ax|Bx|Dx|Ex] gradients are final long before [Q|K|V]'s: their share of dWcat and of g_x = gY1 Wcat is
+  // computed under the attention backward, leaving only the [Q|K|V] share for the tail of the pass
+  const bool split_tail = (opt & 8) && P.gated && P.attn && sd && P.qkv_off > 0 && P.qkv_off < P.Wy && N > 0;
+  auto wcat_wgrad = [&](int64_t r0, int64_t rows) -> int {   // d Wcat[r0 : r0 + rows] (+ bias gradient) on s2
+    GemmParams w;
+    w.M = (int)rows; w.N = (int)d; w.K = (int)N;
+    w.A = P.gY1 + r0; w.lda = (int)P.Wy; w.ta = 1; w.B = a->x; w.ldb = (int)d; w.tb = 1;
+    w.C = P.gWcat + r0 * d; w.ldc = (int)d;
+    w.splitk = splitk_for(N, rows, d) < 2 ? 2 : splitk_for(N, rows, d);
+    w.colsum_a = P.gbcat + r0; w.precision = prec;
+    return N > 0 ? gemm(w, s2) : GPS_OK;
+  };
+
   cudaStream_t se = (P.gated && sd && early_edge) ? sd->s4 : st;   // stream of the edge BatchNorm backward
   // data gradients g_in = g_out W read W through the MN-major planes packed by the forward pass
   auto set_bpt = [&](GemmParams& g, const uint8_t* pt, int64_t cols, int64_t K) {
@@ -920,6 +934,17 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
       set_bpt(g, P.pt_C, d, d);
       GPS_TRY(gemm(g, st));
     }
+    if (split_tail) {
+      const int64_t wl = P.qkv_off;
+      GPS_CUDA(cudaMemsetAsync(P.gWcat, 0, (size_t)(P.Wy * d + P.Wy) * sizeof(float), s2));
+      GPS_TRY(wcat_wgrad(0, wl));
+      GemmParams g;   // g_x = g_xloc + gY1[:, :wl] Wcat[:wl]
+      g.M = (int)N; g.N = (int)d; g.K = (int)wl;
+      g.A = P.gY1; g.lda = (int)P.Wy; g.B = P.Wcat; g.ldb = (int)d; g.tb = 1; g.C = a->grad_x; g.ldc = (int)d;
+      g.R1 = P.g_xloc; g.ldr1 = (int)d; g.precision = prec;
+      set_bpt(g, P.pt_cat, d, P.Wy);
+      GPS_TRY(gemm(g, st));
+    }
     g_x_local = P.g_xloc;  // residual x_in + ...
   } else if (P.gine) {
     // x_loc = x + drop(h1 W1^T + b1)
@@ -953,7 +978,24 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   if (two_branches && sd) GPS_TRY(sd->order(sa, st));
 
   // ---- g_x = [local paths] + [attention residual] + gY1 Wcat ;  d{A,B,D,E,in_proj}
-  if (P.Wy) {
+  if (P.Wy && split_tail) {
+    const int64_t wl = P.qkv_off, wg = P.Wy - P.qkv_off;
+    GPS_TRY(wfork(st));
+    GPS_TRY(wcat_wgrad(wl, wg));
+    PackDesc pdsc = pack_desc(a, P);
+    k_unpack<<<(unsigned)pdsc.total_rows, 128, 0, s2>>>(pdsc, P.gWcat, P.gbcat);
+    GPS_LAUNCH_CHECK();
+    GemmParams g;   // g_x += g_hA + gY1[:, wl:] Wcat[wl:]  (accumulated onto the first share)
+    g.M = (int)N; g.N = (int)d; g.K = (int)wg;
+    g.A = P.gY1 + wl; g.lda = (int)P.Wy; g.B = P.Wcat + wl * d; g.ldb = (int)d; g.tb = 1; g.C = a->grad_x; g.ldc = (int)d;
+    g.R1 = P.g_hA; g.ldr1 = (int)d; g.precision = prec;
+    g.splitk = 2;
+    if (wl % 64 == 0) {
+      set_bpt(g, P.pt_cat, d, P.Wy);
+      g.bpk_kb0 = (int)(wl / 64);
+    }
+    GPS_TRY(gemm(g, st));
+  } else if (P.Wy) {
     GPS_TRY(wfork(st));
     GPS_CUDA(cudaMemsetAsync(P.gWcat, 0, (size_t)(P.Wy * d + P.Wy) * sizeof(float), s2));
     GemmParams w;
