@@ -37,6 +37,8 @@ WORKLOADS = {
     "pcqm4m-small": ("pcqm4m-small", "CustomGatedGCN", "Transformer", 4, 0.0, 0.5, "configs/GPS/pcqm4m-GPS+RWSE.yaml"),
     "zinc-gatedgcn": ("zinc-gatedgcn", "CustomGatedGCN", "Transformer", 4, 0.0, 0.5, "configs/GPS/zinc-GPS+RWSE.yaml"),
     "zinc-gine": ("zinc-gine", "GINE", "Transformer", 4, 0.0, 0.5, "configs/GPS/zinc-GPS+RWSE.yaml"),
+    "zinc-gcn": ("zinc-gine", "GCN", "Transformer", 4, 0.2, 0.0,
+                 "layer settings of configs/GPS/webkb-tex-GPS.yaml (GCN+Transformer d=64 H=4) on the ZINC-shaped batch"),
     "code2": ("code2", "CustomGatedGCN", "Transformer", 4, 0.2, 0.2, "configs/GPS/ogbg-code2-GPS.yaml"),
     "pcqm4m-medium-performer": ("pcqm4m-medium-performer", "CustomGatedGCN", "Performer", 16, 0.1, 0.1,
                                 "configs/GPS/pcqm4m-GPSmedium+RWSE.yaml (Performer as BASELINE.json asks)"),

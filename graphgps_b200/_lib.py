@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgps_b200.so")
 
 GPS_OK, GPS_ERR_ARG, GPS_ERR_UNSUPPORTED, GPS_ERR_CUDA = 0, -1, -2, -3
-LOCAL = {"None": 0, "CustomGatedGCN": 1, "GINE": 2}
+LOCAL = {"None": 0, "CustomGatedGCN": 1, "GINE": 2, "GCN": 3}
 GLOBAL = {"None": 0, "Transformer": 1, "Performer": 2}
 ACT = {"relu": 0, "gelu": 1}
 PRECISION = {"fp32": 0, "bf16": 1}
@@ -60,6 +60,7 @@ class GpsLayerArgs(C.Structure):
         ("saved", _fp), ("saved_bytes", C.c_int64),
         ("workspace", _fp), ("workspace_bytes", C.c_int64),
         ("offset_dev", _fp),
+        ("gcn_conv", GpsLinear),
     ]
 
 
@@ -112,7 +113,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.gps_abi_version() != 1:
+    if lib.gps_abi_version() != 2:
         raise RuntimeError("libgps_b200.so ABI version mismatch")
     _lib = lib
     return lib

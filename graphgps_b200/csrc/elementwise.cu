@@ -263,6 +263,28 @@ struct OpAdd3 {
   __device__ void finish(int, int) {}
 };
 
+// out[c] += sum_r a[r, c]: thread -> CTA (shared memory over threadIdx.y) -> one float atomic per column per CTA
+__global__ void __launch_bounds__(1024) k_colsum(const float* __restrict__ a, int64_t lda, int64_t rows,
+                                                 float* __restrict__ out) {
+  extern __shared__ float4 sm[];
+  const int c4 = threadIdx.x, ry = threadIdx.y, RY = blockDim.y, C4 = blockDim.x;
+  float4 acc = f4zero();
+  for (int64_t r = (int64_t)blockIdx.x * RY + ry; r < rows; r += (int64_t)gridDim.x * RY)
+    acc = f4add(acc, ld4(a + r * lda + c4 * 4));
+  if (RY > 1) {
+    sm[ry * C4 + c4] = acc;
+    __syncthreads();
+    if (ry == 0)
+      for (int y = 1; y < RY; ++y) acc = f4add(acc, sm[y * C4 + c4]);
+  }
+  if (ry == 0) {
+    atomicAdd(out + c4 * 4 + 0, acc.x);
+    atomicAdd(out + c4 * 4 + 1, acc.y);
+    atomicAdd(out + c4 * 4 + 2, acc.z);
+    atomicAdd(out + c4 * 4 + 3, acc.w);
+  }
+}
+
 template <class Op>
 static int launch_rowwise(Op op, int64_t rows, int64_t d, cudaStream_t stream) {
   if (rows == 0) return GPS_OK;
@@ -315,6 +337,15 @@ int add3(const float* a, int64_t lda, const float* b, int64_t ldb, const float* 
          int64_t ldo, int64_t rows, int64_t d, cudaStream_t stream) {
   OpAdd3 op{a, lda, b, ldb, c, ldc, out, ldo};
   return launch_rowwise(op, rows, d, stream);
+}
+
+int colsum(const float* a, int64_t lda, int64_t rows, int64_t d, float* out, cudaStream_t stream) {
+  if (rows == 0) return GPS_OK;
+  RowGeom g;
+  GPS_TRY(row_geom(rows, d, 1, &g));
+  k_colsum<<<g.grid, g.block, g.smem, stream>>>(a, lda, rows, out);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
 }
 
 int copy2d(const float* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int64_t d, cudaStream_t stream) {

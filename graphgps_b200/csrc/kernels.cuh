@@ -79,6 +79,14 @@ int gine_bwd_dst(const GpsGraph& g, int64_t d, const float* x, const float* e, c
 int gine_bwd_src(const GpsGraph& g, int64_t d, const float* g_e, const float* g_o, float eps, const float* add,
                  float* g_x, cudaStream_t stream);
 
+// GCN (PyG GCNConv): dinv_i = (1 + #non-self in-edges)^-1/2; x_loc = x + drop(b + A_hat Y) [+ column sums of x_loc];
+// backward gY = A_hat^T g_h
+int gcn_dinv(const GpsGraph& g, float* dinv, cudaStream_t stream);
+int gcn_fwd(const GpsGraph& g, int64_t d, const float* Y, int64_t ldy, const float* dinv, const float* bias,
+            const float* x, float* xloc, DropCfg drop, double* stats, cudaStream_t stream);
+int gcn_bwd(const GpsGraph& g, int64_t d, const float* g_h, const float* dinv, float* gY, int64_t ldg,
+            cudaStream_t stream);
+
 // ---- attention ------------------------------------------------------------------------------
 int attention_fwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, const float* K, const float* V,
                   int64_t ld, float* O, int64_t ldo, float* lse, float p_drop, uint64_t seed, uint64_t offset,

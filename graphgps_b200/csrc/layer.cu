@@ -160,7 +160,7 @@ enum { BN_X = 0, BN_E = 1, BN_L = 2, BN_A = 3, BN_2 = 4, BN_COUNT = 5 };
 
 struct Plan {
   int64_t N, E, d, H, hd, Wy, qkv_off;
-  bool gated, gine, attn, perf;
+  bool gated, gine, gcn, attn, perf;
   int64_t inner, mp, m;   // Performer: H*64, padded / real feature count
   float *pQ, *pK, *pV, *pfq, *pfk, *pPn, *pgmax;   // saved (Performer)
   int *pargq, *pargk, *pnmax;
@@ -170,6 +170,7 @@ struct Plan {
   // saved
   float *Wcat, *bcat, *Y1, *ehat, *xt, *xloc, *O, *lse, *hA, *s, *hid, *hid_pre, *t, *bnbuf;
   float *agg, *h1, *h1_pre;
+  float* dinv;   // GCN: deg^-1/2 per node
   // pre-packed bf16 hi/lo weight planes for the forward GEMMs (bulk-TMA B operand)
   uint8_t *pk_cat, *pk_C, *pk_out, *pk_ff1, *pk_ff2, *pk_g0, *pk_g1;
   // the same weights as MN-major planes for the data-gradient GEMMs of the backward pass (training only)
@@ -198,7 +199,8 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
               (long long)a->d);
   P->gated = a->local_type == GPS_LOCAL_GATEDGCN;
   P->gine = a->local_type == GPS_LOCAL_GINE;
-  GPS_REQUIRE(a->local_type == GPS_LOCAL_NONE || P->gated || P->gine, GPS_ERR_ARG, "unknown local_type %d",
+  P->gcn = a->local_type == GPS_LOCAL_GCN;
+  GPS_REQUIRE(a->local_type == GPS_LOCAL_NONE || P->gated || P->gine || P->gcn, GPS_ERR_ARG, "unknown local_type %d",
               a->local_type);
   GPS_REQUIRE(a->global_type == GPS_GLOBAL_NONE || a->global_type == GPS_GLOBAL_TRANSFORMER ||
                   a->global_type == GPS_GLOBAL_PERFORMER,
@@ -223,7 +225,7 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
   GPS_REQUIRE(a->dropout >= 0.f && a->dropout < 1.f && a->attn_dropout >= 0.f && a->attn_dropout < 1.f,
               GPS_ERR_ARG, "dropout probabilities must be in [0,1)");
   const int64_t N = P->N, E = P->E, d = P->d;
-  P->qkv_off = P->gated ? 4 * d : 0;
+  P->qkv_off = P->gated ? 4 * d : (P->gcn ? d : 0);
   P->Wy = P->qkv_off + (P->attn ? 3 * d : 0);
   const bool gelu = a->act == GPS_ACT_GELU;
 
@@ -243,7 +245,8 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
     P->h1 = S.alloc<float>(N * d);
     if (gelu) P->h1_pre = S.alloc<float>(N * d);
   }
-  if (P->gated || P->gine) P->xloc = S.alloc<float>(N * d);
+  if (P->gcn) P->dinv = S.alloc<float>(N);
+  if (P->gated || P->gine || P->gcn) P->xloc = S.alloc<float>(N * d);
   if (P->attn) {
     P->O = S.alloc<float>(N * d);
     P->lse = S.alloc<float>(N * P->H);
@@ -313,7 +316,7 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
     P->g_tmp2 = Bk.alloc<float>(N * d);
     P->g_tmp3 = Bk.alloc<float>(N * d);
   }
-  if (P->gated || P->gine) P->g_xloc = Bk.alloc<float>(N * d);
+  if (P->gated || P->gine || P->gcn) P->g_xloc = Bk.alloc<float>(N * d);
   if (P->attn) {
     P->g_hA = Bk.alloc<float>(N * d);
     P->g_O = Bk.alloc<float>(N * d);
@@ -393,6 +396,10 @@ static PackDesc pack_desc(const GpsLayerArgs* a, const Plan& P) {
     add(a->gcn_D, (int)P.d);
     add(a->gcn_E, (int)P.d);
   }
+  if (P.gcn) {   // GCNConv.lin has no bias; GCNConv.bias is added after the aggregation (scatter.cu)
+    pd.seg[pd.nseg++] = PackSeg{a->gcn_conv.weight, nullptr, a->gcn_conv.grad_weight, nullptr, (int)P.d};
+    pd.total_rows += (int)P.d;
+  }
   if (P.attn) add(a->attn_in, (int)(3 * P.d));
   return pd;
 }
@@ -408,7 +415,7 @@ static int check_bn(const GpsBatchNorm& b, const char* name) {
 }
 
 static int check_params(const GpsLayerArgs* a, const Plan& P) {
-  GPS_REQUIRE(a->x && (P.E == 0 || a->edge_attr || a->local_type == GPS_LOCAL_NONE), GPS_ERR_ARG,
+  GPS_REQUIRE(a->x && (P.E == 0 || a->edge_attr || !(P.gated || P.gine)), GPS_ERR_ARG,
               "missing x / edge_attr");
   if (P.gated) {
     GPS_TRY(check_linear(a->gcn_A, "local_model.A", true));
@@ -423,7 +430,8 @@ static int check_params(const GpsLayerArgs* a, const Plan& P) {
     GPS_TRY(check_linear(a->gine_lin0, "local_model.nn.0", true));
     GPS_TRY(check_linear(a->gine_lin1, "local_model.nn.2", true));
   }
-  if (P.gated || P.gine) GPS_TRY(check_bn(a->norm1_local, "norm1_local"));
+  if (P.gcn) GPS_TRY(check_linear(a->gcn_conv, "local_model.lin / local_model.bias", true));
+  if (P.gated || P.gine || P.gcn) GPS_TRY(check_bn(a->norm1_local, "norm1_local"));
   if (P.attn) {
     GPS_TRY(check_linear(a->attn_in, "self_attn.in_proj", true));
     GPS_TRY(check_linear(a->attn_out, "self_attn.out_proj", true));
@@ -507,7 +515,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
   if (train) GPS_CUDA(cudaMemsetAsync(P.fstats, 0, (size_t)BN_COUNT * 2 * d * sizeof(double), st));
   Side* sd = side_stream();
   cudaStream_t s2 = sd ? sd->s : st;
-  const bool two_branches = (P.gated || P.gine) && (P.attn || P.perf);
+  const bool two_branches = (P.gated || P.gine || P.gcn) && (P.attn || P.perf);
 
   // weights: concatenate the node projections, then pre-pack every forward weight into the tcgen05 kernel's
   // shared-memory tile image (bf16 hi/lo planes) so its B operand arrives by bulk TMA
@@ -624,6 +632,10 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g2.precision = a->precision;
     set_bpk(g2, P.pk_g1, d, d, 0);
     GPS_TRY(gemm(g2, st));
+  } else if (P.gcn) {
+    // x_loc = x + drop(GCNConv(x))  (gps_layer.py:49-51,186-189); Y = x W^T is column block 0 of Y1
+    GPS_TRY(gcn_dinv(a->graph, P.dinv, st));
+    GPS_TRY(gcn_fwd(a->graph, d, P.Y1, P.Wy, P.dinv, a->gcn_conv.bias, a->x, P.xloc, drop(GPS_SITE_LOCAL), stats(BN_L), st));
   }
 
   // ---- global attention  (gps_layer.py:198-218, 234-241)
@@ -683,7 +695,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
 
   // ---- s = norm1_local(x_loc) + norm1_attn(hA)   (gps_layer.py:194,217,222)
   {
-    const bool loc = P.gated || P.gine;
+    const bool loc = P.gated || P.gine || P.gcn;
     const float* first = loc ? P.xloc : P.hA;
     BnView bf = loc ? bn_view_fwd(P, a, BN_L, a->norm1_local, N) : bn_view_fwd(P, a, BN_A, a->norm1_attn, N);
     const float* second = (loc && (P.attn || P.perf)) ? P.hA : nullptr;
@@ -747,7 +759,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   Side* sd = side_stream();
   cudaStream_t s2 = sd ? sd->s : st;
   auto wfork = [&](cudaStream_t from) -> int { return sd ? sd->order(from, s2) : GPS_OK; };
-  const bool two_branches = (P.gated || P.gine) && (P.attn || P.perf);
+  const bool two_branches = (P.gated || P.gine || P.gcn) && (P.attn || P.perf);
   cudaStream_t sa = (two_branches && sd) ? sd->s3 : st;   // stream of the attention-branch backward
   const int opt = opt_flags();
   const bool early_edge = (opt & 4) != 0;
@@ -825,7 +837,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(gemm(g2, st));
   }
 
-  const bool loc = P.gated || P.gine;
+  const bool loc = P.gated || P.gine || P.gcn;
   // ---- norm1_local / norm1_attn (gps_layer.py:194,217): g_xloc, g_hA
   if (loc) {
     BnView v = bn_view(P, BN_L, a->norm1_local);
@@ -973,6 +985,19 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(gine_bwd_dst(a->graph, d, a->x, a->edge_attr, P.g_agg, a->grad_edge_attr, st));
     GPS_TRY(gine_bwd_src(a->graph, d, a->grad_edge_attr, P.g_agg, a->gine_eps, P.g_xloc, P.g_xl, st));
     g_x_local = P.g_xl;
+  } else if (P.gcn) {
+    // x_loc = x + drop(b + A_hat Y): g_h = drop * g_xloc; g_b = colsum(g_h); gY = A_hat^T g_h -> gY1[:, 0:d]
+    const float* g_h = P.g_xloc;
+    if (pd > 0.f) {
+      GPS_TRY(dropmul(P.g_xloc, P.g_tmp3, N, d, P, a, GPS_SITE_LOCAL, st));
+      g_h = P.g_tmp3;
+    }
+    if (a->gcn_conv.grad_bias) {
+      if (!g_grads_prezeroed) GPS_CUDA(cudaMemsetAsync(a->gcn_conv.grad_bias, 0, (size_t)d * sizeof(float), st));
+      GPS_TRY(colsum(g_h, d, N, d, a->gcn_conv.grad_bias, st));
+    }
+    GPS_TRY(gcn_bwd(a->graph, d, g_h, P.dinv, P.gY1, P.Wy, st));
+    g_x_local = P.g_xloc;
   }
 
   if (two_branches && sd) GPS_TRY(sd->order(sa, st));

@@ -5,6 +5,8 @@
 //   x~_i = Ax_i + (sum_j sigma_ij * Bx_j) / (sum_j sigma_ij + 1e-6)
 // GINE aggregate (PyG GINEConv; maths per graphgps/layer/gine_conv_layer.py:56-84):
 //   out_i = (1+eps) x_i + sum_j relu(x_j + e_ij)
+// GCN aggregate (PyG 2.2 GCNConv, gps_layer.py:49-51; gcn_norm with add_remaining_self_loops, unit edge weights):
+//   deg_i = 1 + #{j -> i, j != i};  h_i = b + deg_i^-1/2 ( deg_i^-1/2 Y_i + sum_{j -> i, j != i} deg_j^-1/2 Y_j ),  Y = x W^T
 // The reference materialises three [E,d] gathers and runs two atomic torch_scatter sums
 // (gatedgcn_layer.py:118-123).  Here a thread owns (node, 4 channels): it walks the node's
 // dst-sorted (or src-sorted) edge segment with 128-bit loads, reduces serially in registers — no
@@ -237,7 +239,96 @@ __global__ void k_gine_bwd_src(GpsGraph g, int d, const float* __restrict__ g_e,
   }
 }
 
+// ---- GCN (symmetric-normalised adjacency with one unit self loop per node)
+__global__ void k_gcn_dinv(GpsGraph g, float* __restrict__ dinv) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.N) return;
+  int deg = 1;   // the self loop; existing self-loop edges are replaced by it (add_remaining_self_loops)
+  for (int k = g.dst_ptr[i]; k < g.dst_ptr[i + 1]; ++k) deg += g.dst_src[k] != (int)i;
+  dinv[i] = rsqrtf((float)deg);
+}
+
+// x_loc_i = x_i + drop(b + dinv_i (dinv_i Y_i + sum_{j->i, j != i} dinv_j Y_j))  [+ column sums of x_loc]
+template <bool STATS>
+__global__ void __launch_bounds__(1024) k_gcn_fwd(GpsGraph g, int d, const float* __restrict__ Y, int64_t ldy,
+                                                  const float* __restrict__ dinv, const float* __restrict__ bias,
+                                                  const float* __restrict__ x, float* __restrict__ xloc, DropCfg drop,
+                                                  double* stats) {
+  extern __shared__ float4 sm[];
+  const int c = threadIdx.x * 4, ry = threadIdx.y, RY = blockDim.y;
+  const uint64_t offs = drop.offset + ((drop.p > 0.f && drop.offset_dev) ? *drop.offset_dev : 0ull);
+  const float4 b4 = ld4(bias + c);
+  float4 acc[2] = {f4zero(), f4zero()};
+  for (int64_t i = (int64_t)blockIdx.x * RY + ry; i < g.N; i += (int64_t)gridDim.x * RY) {
+    const float di = dinv[i];
+    float4 a = f4scale(ld4(Y + i * ldy + c), di);
+    for (int k = g.dst_ptr[i]; k < g.dst_ptr[i + 1]; ++k) {
+      const int j = g.dst_src[k];
+      if (j == (int)i) continue;
+      a = f4fma(make_float4(dinv[j], dinv[j], dinv[j], dinv[j]), ld4(Y + (int64_t)j * ldy + c), a);
+    }
+    float4 h = f4add(f4scale(a, di), b4);
+    if (drop.p > 0.f) h = f4mul(h, dropout_scale4(drop.p, drop.seed, offs, drop.site, ((uint64_t)i * (uint64_t)d + c) >> 2));
+    const float4 v = f4add(ld4(x + i * d + c), h);
+    st4(xloc + i * d + c, v);
+    if (STATS) {
+      acc[0] = f4add(acc[0], v);
+      acc[1] = f4fma(v, v, acc[1]);
+    }
+  }
+  if (STATS) {
+    double* ptrs[2] = {stats, stats + d};
+    block_stats<2>(acc, ptrs, sm);
+  }
+}
+
+// gY_j = dinv_j (dinv_j g_h_j + sum_{j->i, i != j} dinv_i g_h_i)   (the adjoint of the aggregation above)
+__global__ void k_gcn_bwd(GpsGraph g, int d, const float* __restrict__ g_h, const float* __restrict__ dinv,
+                          float* __restrict__ gY, int64_t ldg) {
+  const int c = threadIdx.x * 4, ry = threadIdx.y, RY = blockDim.y;
+  for (int64_t j = (int64_t)blockIdx.x * RY + ry; j < g.N; j += (int64_t)gridDim.x * RY) {
+    const float dj = dinv[j];
+    float4 a = f4scale(ld4(g_h + j * d + c), dj);
+    for (int k = g.src_ptr[j]; k < g.src_ptr[j + 1]; ++k) {
+      const int i = g.src_dst[k];
+      if (i == (int)j) continue;
+      a = f4fma(make_float4(dinv[i], dinv[i], dinv[i], dinv[i]), ld4(g_h + (int64_t)i * d + c), a);
+    }
+    st4(gY + j * ldg + c, f4scale(a, dj));
+  }
+}
+
 }  // namespace
+
+int gcn_dinv(const GpsGraph& g, float* dinv, cudaStream_t stream) {
+  if (g.N == 0) return GPS_OK;
+  k_gcn_dinv<<<(unsigned)ceil_div(g.N, (int64_t)256), 256, 0, stream>>>(g, dinv);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+int gcn_fwd(const GpsGraph& g, int64_t d, const float* Y, int64_t ldy, const float* dinv, const float* bias,
+            const float* x, float* xloc, DropCfg drop, double* stats, cudaStream_t stream) {
+  if (g.N == 0) return GPS_OK;
+  NodeGeom ng;
+  GPS_TRY(node_geom(g.N, d, stats ? 2 : 0, &ng));
+  if (stats)
+    k_gcn_fwd<true><<<ng.grid, ng.block, ng.smem, stream>>>(g, (int)d, Y, ldy, dinv, bias, x, xloc, drop, stats);
+  else
+    k_gcn_fwd<false><<<ng.grid, ng.block, 0, stream>>>(g, (int)d, Y, ldy, dinv, bias, x, xloc, drop, nullptr);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+int gcn_bwd(const GpsGraph& g, int64_t d, const float* g_h, const float* dinv, float* gY, int64_t ldg,
+            cudaStream_t stream) {
+  if (g.N == 0) return GPS_OK;
+  NodeGeom ng;
+  GPS_TRY(node_geom(g.N, d, 0, &ng));
+  k_gcn_bwd<<<ng.grid, ng.block, 0, stream>>>(g, (int)d, g_h, dinv, gY, ldg);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
 
 int gatedgcn_fwd(const GpsGraph& g, int64_t d, const float* Ax, const float* Bx, const float* Dx, const float* Ex,
                  int64_t ldy, float* Ce, float* xt, double* stats_x, double* stats_e, cudaStream_t stream) {

@@ -20,8 +20,9 @@ import torch.nn as nn
 from . import _lib
 from .graph import graph_of
 
-_SUPPORTED_LOCAL = ("None", "CustomGatedGCN", "GINE")
-_KNOWN_LOCAL = _SUPPORTED_LOCAL + ("GCN", "GIN", "GENConv", "GAT", "PNA")
+_SUPPORTED_LOCAL = ("None", "CustomGatedGCN", "GINE", "GCN")
+_EDGE_LOCAL = ("CustomGatedGCN", "GINE")   # local models that read batch.edge_attr (gps_layer.py:44-53)
+_KNOWN_LOCAL = _SUPPORTED_LOCAL + ("GIN", "GENConv", "GAT", "PNA")
 _SUPPORTED_GLOBAL = ("None", "Transformer", "Performer")
 _KNOWN_GLOBAL = _SUPPORTED_GLOBAL + ("BiasedTransformer", "BigBird")
 _ACT_MODULES = {"relu": nn.ReLU, "gelu": nn.GELU}
@@ -73,6 +74,16 @@ class _GINEParams(nn.Module):
         super().__init__()
         self.nn = nn.Sequential(nn.Linear(dim, dim), _ACT_MODULES[act](), nn.Linear(dim, dim))
         self.register_buffer("eps", torch.Tensor([0.0]))
+
+
+class _GCNConvParams(nn.Module):
+    """Names of PyG 2.2 GCNConv(dim_h, dim_h) as built at gps_layer.py:49-51: lin.weight (no bias, glorot), bias (zeros)."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.lin = nn.Linear(dim, dim, bias=False)
+        nn.init.xavier_uniform_(self.lin.weight)       # PyG Linear(weight_initializer='glorot')
+        self.bias = nn.Parameter(torch.zeros(dim))
 
 
 def _orthogonal_gaussian_matrix(nb_rows, nb_cols):
@@ -176,7 +187,7 @@ class _GPSLayerFn(torch.autograd.Function):
         if g_e_out is not None:
             g_e_out = g_e_out.contiguous()
         g_x = torch.empty_like(x)
-        g_e = torch.empty_like(e) if layer.local_gnn_type != "None" else None
+        g_e = torch.empty_like(e) if layer.local_gnn_type in _EDGE_LOCAL else None
         plan = layer._plan(args, gs)
         ws = _workspace(dev, plan[1])
         args.x, args.edge_attr = x.data_ptr(), _lib.ptr(e)
@@ -239,6 +250,9 @@ class GPSLayer(nn.Module):
             self.local_model = None
         elif local_gnn_type == "GINE":
             self.local_model = _GINEParams(dim_h, act)
+        elif local_gnn_type == "GCN":
+            self.local_gnn_with_edge_attr = False
+            self.local_model = _GCNConvParams(dim_h)
         else:
             self.local_model = _GatedGCNParams(dim_h)
         self.local_gnn_type = local_gnn_type
@@ -343,6 +357,9 @@ class GPSLayer(nn.Module):
         elif self.local_gnn_type == "GINE":
             a.gine_lin0, a.gine_lin1 = lin("local_model.nn.0"), lin("local_model.nn.2")
             a.gine_eps = float(self._gine_eps_host)
+        elif self.local_gnn_type == "GCN":
+            a.gcn_conv = _lin(named["local_model.lin.weight"], named["local_model.bias"],
+                              g.get("local_model.lin.weight"), g.get("local_model.bias"))
         if self.global_model_type == "Transformer":
             a.attn_in = _lin(named["self_attn.in_proj_weight"], named["self_attn.in_proj_bias"],
                              g.get("self_attn.in_proj_weight"), g.get("self_attn.in_proj_bias"))
@@ -377,7 +394,7 @@ class GPSLayer(nn.Module):
             raise TypeError("batch.x must be float32")
         x = x.contiguous()
         e = getattr(batch, "edge_attr", None)
-        if self.local_gnn_type != "None":
+        if self.local_gnn_type in _EDGE_LOCAL:
             if e is None or e.shape[-1] != self.dim_h:
                 raise ValueError("Node and edge feature dimensionalities do not match")
             e = e.contiguous()

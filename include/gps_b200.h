@@ -31,12 +31,12 @@
 extern "C" {
 #endif
 
-#define GPS_ABI_VERSION 1
+#define GPS_ABI_VERSION 2
 
 enum { GPS_OK = 0, GPS_ERR_ARG = -1, GPS_ERR_UNSUPPORTED = -2, GPS_ERR_CUDA = -3 };
 
 /* local_gnn_type / global_model_type of GPSLayer.__init__ (gps_layer.py:20-24,44-122) */
-enum { GPS_LOCAL_NONE = 0, GPS_LOCAL_GATEDGCN = 1, GPS_LOCAL_GINE = 2 };
+enum { GPS_LOCAL_NONE = 0, GPS_LOCAL_GATEDGCN = 1, GPS_LOCAL_GINE = 2, GPS_LOCAL_GCN = 3 };
 enum { GPS_GLOBAL_NONE = 0, GPS_GLOBAL_TRANSFORMER = 1, GPS_GLOBAL_PERFORMER = 2 };
 /* register.act_dict keys used by shipped configs (gps_layer.py:33) */
 enum { GPS_ACT_RELU = 0, GPS_ACT_GELU = 1 };
@@ -158,6 +158,10 @@ typedef struct {
   /* optional device-resident addend for `offset` (uint64 on the device, read by the kernels at run time):
    * lets a captured CUDA graph draw fresh dropout masks on every replay. NULL = use `offset` only. */
   const uint64_t* offset_dev;
+
+  /* ABI 2: PyG GCNConv(dim_h, dim_h) local model (gps_layer.py:49-51): weight = local_model.lin.weight [d,d]
+   * (its Linear has no bias), bias = local_model.bias [d], added after the normalised aggregation. */
+  GpsLinear gcn_conv;
 } GpsLayerArgs;
 
 typedef struct {

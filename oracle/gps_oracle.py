@@ -17,6 +17,10 @@ What is restated, each following the cited reference lines (paths relative to /r
   * GPSLayer.forward composition ............ graphgps/layer/gps_layer.py:155-232, 234-257
   * GatedGCNLayer forward/message/aggregate . graphgps/layer/gatedgcn_layer.py:45-136
   * GINEConv (PyG 2.2, third party) ......... maths evidenced by graphgps/layer/gine_conv_layer.py:56-84
+  * GCNConv (PyG 2.2, third party, source not under /root/reference; call site gps_layer.py:49-51,186):
+                                              published algorithm (Kipf & Welling; PyG gcn_norm with
+                                              add_remaining_self_loops) -- pinned only to oracle/ref_shim.py's
+                                              message-passing restatement of the same algorithm, not to PyG itself
   * to_dense_batch (PyG 2.2, third party) ... SURVEY.md Appendix A; call site gps_layer.py:199
   * Performer SelfAttention / FAVOR+ ........ graphgps/layer/performer_layer.py:119-144 (softmax_kernel),
                                               :163-195 (projection), :200-205 (linear_attention),
@@ -102,6 +106,29 @@ class OracleGINE(nn.Module):
         return self.nn(out)
 
 
+class OracleGCN(nn.Module):
+    """PyG 2.2 GCNConv(dim, dim) with default arguments as built at gps_layer.py:49-51:
+    h = D^-1/2 (A' + I) D^-1/2 (x W^T) + b, A' = adjacency without self loops, D = 1 + in-degree under A'."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.lin = nn.Linear(dim, dim, bias=False)
+        nn.init.xavier_uniform_(self.lin.weight)
+        self.bias = nn.Parameter(torch.zeros(dim))
+
+    def forward(self, x, edge_index, edge_attr=None):
+        N = x.shape[0]
+        src, dst = edge_index[0], edge_index[1]
+        keep = src != dst
+        src, dst = src[keep], dst[keep]
+        deg = torch.ones(N, dtype=x.dtype).index_add_(0, dst, torch.ones(dst.shape[0], dtype=x.dtype))
+        dinv = deg.rsqrt()
+        y = self.lin(x)
+        agg = (dinv * dinv).unsqueeze(1) * y                                        # the self loop
+        agg = agg.index_add(0, dst, (dinv[src] * dinv[dst]).unsqueeze(1) * y[src])
+        return agg + self.bias
+
+
 def gaussian_orthogonal_random_matrix(nb_rows, nb_columns, generator=None):
     """performer_layer.py:163-195 (scaling=0)."""
     blocks = []
@@ -177,7 +204,7 @@ class OraclePerformerSelfAttention(nn.Module):
 
 class OracleGPSLayer(nn.Module):
     """Restatement of graphgps/layer/gps_layer.py:16-257 for
-    local in {None, GINE, CustomGatedGCN} x global in {None, Transformer, Performer}, BatchNorm."""
+    local in {None, GINE, GCN, CustomGatedGCN} x global in {None, Transformer, Performer}, BatchNorm."""
 
     def __init__(self, dim_h, local_gnn_type, global_model_type, num_heads, act="relu",
                  pna_degrees=None, equivstable_pe=False, dropout=0.0, attn_dropout=0.0,
@@ -191,6 +218,8 @@ class OracleGPSLayer(nn.Module):
             self.local_model = None
         elif local_gnn_type == "GINE":
             self.local_model = OracleGINE(dim_h, act)
+        elif local_gnn_type == "GCN":
+            self.local_model = OracleGCN(dim_h)
         elif local_gnn_type == "CustomGatedGCN":
             self.local_model = OracleGatedGCN(dim_h, dropout, act)
         else:

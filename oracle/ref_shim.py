@@ -23,6 +23,12 @@ Stub semantics follow SURVEY.md Appendix A:
     aggregation index = edge_index[1], dim_size = N  (PyG default flow source_to_target)
   * GINEConv(nn, eps=0): out = nn((1+eps) x_i + sum_j relu(x_j + e_ij)); eps is a buffer
   * to_dense_batch: zero padded [B, Nmax, d] + bool mask
+  * GCNConv(in, out) (PyG 2.2 defaults: improved=False, add_self_loops=True, normalize=True, bias=True):
+    x' = lin(x) (Linear without bias, glorot); gcn_norm = add_remaining_self_loops (unit weights; an existing
+    self-loop edge is replaced by the single loop of weight 1), deg = scatter_add(w, col), norm = deg^-1/2[row]
+    * w * deg^-1/2[col]; out = sum_{j->i} norm_ij x'_j + bias.  PyG's source is NOT under /root/reference
+    (third party, README.md:15,25 pins pyg=2.2): this variant is pinned only to this restatement of the
+    published algorithm, cross-checked against the independent dense restatement in gps_oracle.OracleGCN.
 """
 from __future__ import annotations
 
@@ -140,6 +146,44 @@ class _GINEConv(_MessagePassing):
         return (x_j + edge_attr).relu()
 
 
+class _GCNConv(_MessagePassing):
+    """PyG 2.2 GCNConv with default arguments (call site gps_layer.py:49-51, :186)."""
+
+    def __init__(self, in_channels, out_channels, improved=False, cached=False, add_self_loops=True,
+                 normalize=True, bias=True, **kw):
+        super().__init__(aggr="add")
+        assert not improved and not cached and add_self_loops and normalize and bias
+        self.lin = _PygLinear(in_channels, out_channels, bias=False)
+        nn.init.xavier_uniform_(self.lin.weight)                 # weight_initializer='glorot'
+        self.bias = nn.Parameter(torch.zeros(out_channels))      # inits.zeros
+
+    @staticmethod
+    def gcn_norm(edge_index, num_nodes, dtype):
+        row, col = edge_index[0], edge_index[1]
+        w = torch.ones(edge_index.shape[1], dtype=dtype)
+        keep = row != col                                        # add_remaining_self_loops(fill_value=1.)
+        loop_w = torch.ones(num_nodes, dtype=dtype)
+        loop_w[row[~keep]] = w[~keep]
+        loops = torch.arange(num_nodes, dtype=edge_index.dtype)
+        edge_index = torch.cat([edge_index[:, keep], torch.stack([loops, loops])], dim=1)
+        w = torch.cat([w[keep], loop_w])
+        row, col = edge_index[0], edge_index[1]
+        deg = _scatter(w, col, 0, None, num_nodes, "sum")
+        dis = deg.pow(-0.5)
+        dis = dis.masked_fill(dis == float("inf"), 0)
+        return edge_index, dis[row] * w * dis[col]
+
+    def forward(self, x, edge_index, edge_weight=None):
+        assert edge_weight is None
+        edge_index, edge_weight = self.gcn_norm(edge_index, x.shape[0], x.dtype)
+        x = self.lin(x)
+        out = self.propagate(edge_index, x=x, edge_weight=edge_weight, size=None)
+        return out + self.bias
+
+    def message(self, x_j, edge_weight):
+        return edge_weight.view(-1, 1) * x_j
+
+
 def _to_dense_batch(x, batch):
     B = int(batch.max()) + 1 if batch.numel() else 0
     n = torch.bincount(batch, minlength=B)
@@ -190,7 +234,7 @@ def load_reference(layer_dir=None):
     conv = _mod("torch_geometric.nn.conv", MessagePassing=_MessagePassing)
     norm = _mod("torch_geometric.nn.norm", LayerNorm=None)
     inits = _mod("torch_geometric.nn.inits", reset=lambda m: None)
-    pygnn = _mod("torch_geometric.nn", Linear=_PygLinear, GINEConv=_GINEConv, GCNConv=None,
+    pygnn = _mod("torch_geometric.nn", Linear=_PygLinear, GINEConv=_GINEConv, GCNConv=_GCNConv,
                  GINConv=None, GENConv=None, GATConv=None, PNAConv=None, conv=conv, norm=norm,
                  inits=inits)
     data = _mod("torch_geometric.data", Batch=_Batch)

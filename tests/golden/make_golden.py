@@ -33,6 +33,10 @@ CASES = [
     ("gatedgcn_transformer_eval", "CustomGatedGCN", "Transformer", "zinc-gatedgcn", 64, 4, "relu", 6, False),
     ("gatedgcn_performer_relu", "CustomGatedGCN", "Performer", "zinc-gatedgcn", 64, 4, "relu", 6, True),
     ("code2_gatedgcn_transformer", "CustomGatedGCN", "Transformer", "code2", 32, 4, "relu", 3, True),
+    # GCN: the aggregation is PyG's GCNConv (third party) as restated in oracle/ref_shim.py; the composition is the
+    # reference's own gps_layer.py
+    ("gcn_transformer_relu", "GCN", "Transformer", "zinc-gine", 64, 4, "relu", 6, True),
+    ("gcn_transformer_hd76", "GCN", "Transformer", "pcqm4m-small", 152, 2, "gelu", 8, True),
 ]
 
 
@@ -47,6 +51,8 @@ def run_case(ref, name, local, glob, shape, d, heads, act, B, training):
                 m.bias.uniform_(-0.3, 0.3)
                 m.running_mean.uniform_(-0.2, 0.2)
                 m.running_var.uniform_(0.6, 1.4)
+        if local == "GCN":
+            layer.local_model.bias.uniform_(-0.3, 0.3)   # PyG initialises it to zero
     state = {k: v.clone() for k, v in layer.state_dict().items()}
     batch = make_batch(shape, seed=11, dim=d, num_graphs=B)
     fix = {"config": dict(name=name, local=local, glob=glob, d=d, heads=heads, act=act, training=training),
@@ -82,7 +88,10 @@ def run_case(ref, name, local, glob, shape, d, heads, act, B, training):
 
 def main():
     ref = load_reference("/root/reference/graphgps/layer")
+    only = set(sys.argv[1:])   # optional: regenerate just the named fixtures
     for case in CASES:
+        if only and case[0] not in only:
+            continue
         fix = run_case(ref, *case)
         path = os.path.join(HERE, case[0] + ".pt")
         torch.save(fix, path)

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"libgps_b200.so does not export {s}"
         assert s in _lib.SYMBOLS, f"ctypes binding missing for {s}"
-    assert lib.gps_abi_version() == 1
+    assert lib.gps_abi_version() == 2
     assert lib.gps_build_arch() == b"sm_100a"
 
 
@@ -38,7 +38,7 @@ def test_graph_bytes_is_pure():
 
 @pytest.mark.parametrize("local,glob", [("CustomGatedGCN", "Transformer"), ("GINE", "Transformer"),
                                         ("CustomGatedGCN", "Performer"), ("None", "Transformer"),
-                                        ("GINE", "None"), ("CustomGatedGCN", "None")])
+                                        ("GINE", "None"), ("CustomGatedGCN", "None"), ("GCN", "Transformer")])
 def test_state_dict_layout_matches_reference(local, glob):
     ours = graphgps_b200.GPSLayer(64, local, glob, 4)
     ref = OracleGPSLayer(64, local, glob, 4)   # same keys as the reference (tests/test_oracle.py pins that)

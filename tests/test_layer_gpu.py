@@ -174,7 +174,9 @@ def test_layer_matches_golden(name, precision):
                                                     ("code2", "CustomGatedGCN", "Transformer", 4),
                                                     ("pcqm4m-medium-performer", "CustomGatedGCN", "Performer", 16),
                                                     ("zinc-gatedgcn", "None", "Performer", 4),
-                                                    ("code2", "CustomGatedGCN", "Performer", 4)])
+                                                    ("code2", "CustomGatedGCN", "Performer", 4),
+                                                    ("pcqm4m-small", "GCN", "Transformer", 4),
+                                                    ("zinc-gine", "GCN", "Performer", 4)])
 def test_layer_matches_oracle_full_size(shape, local, glob, heads):
     """BASELINE-size batch: CUDA layer vs the oracle on the same seeded inputs and weights.
 
@@ -260,6 +262,46 @@ def test_empty_graphs_isolated_nodes_and_no_edges():
     tgt = {k: ref[k] for k in ("out_x", "out_e", "grad_x", "grad_e")}
     tgt["grad_params"], tgt["state_after"] = ref["grad_params"], ref["state_after"]
     compare(res, tgt, 1e-3, "edge cases", grad_l2_tol=5e-3)
+
+
+def test_gcn_self_loops_duplicates_isolated_nodes_and_dropout_consistency():
+    """GCN local model (gps_layer.py:49-51): explicit self-loop edges are replaced by the single unit loop
+    (add_remaining_self_loops), duplicate edges count twice, isolated nodes and an empty graph are handled; then,
+    with dropout on and the Philox offset pinned, backward equals a finite difference of forward (GELU)."""
+    torch.manual_seed(4)
+    d = 32
+    b = batch_from_lists([5, 0, 1, 4], [[(0, 1), (1, 0), (1, 1), (2, 2), (2, 3), (3, 2), (0, 1)], [], [], [(0, 1), (3, 3)]], d=d)
+    ora = OracleGPSLayer(d, "GCN", "Transformer", 4)
+    with torch.no_grad():
+        ora.local_model.bias.uniform_(-0.5, 0.5)
+    ours = graphgps_b200.GPSLayer(d, "GCN", "Transformer", 4)
+    ours.load_state_dict(ora.state_dict(), strict=True)
+    ours = ours.to(DEV)
+    g = torch.Generator().manual_seed(1)
+    fix = {"config": dict(local="GCN"), "ct_x": torch.randn(b.x.shape, generator=g)}
+    ref = run_layer(ora.double(), _to(b.clone(), "cpu", torch.float64), fix)
+    res = run_layer(ours, b.clone().to(DEV), fix)
+    tgt = {k: ref[k] for k in ("out_x", "grad_x")}
+    tgt["grad_params"], tgt["state_after"] = ref["grad_params"], ref["state_after"]
+    compare(res, tgt, 1e-3, "GCN edge cases", grad_l2_tol=5e-3)
+
+    layer = graphgps_b200.GPSLayer(64, "GCN", "Transformer", 4, act="gelu", dropout=0.2, attn_dropout=0.0).to(DEV).train()
+    bb = make_batch("zinc-gine", seed=3, dim=64, num_graphs=12).to(DEV)
+    ct = torch.randn(bb.x.shape, generator=g).to(DEV)
+    vx = torch.randn(bb.x.shape, generator=g).to(DEV)
+
+    def f(x):
+        _set_dropout_counter(11 * 4096)
+        out = layer(graphgps_b200.GraphBatch(x=x, edge_index=bb.edge_index, edge_attr=bb.edge_attr, batch=bb.batch,
+                                             num_graphs=bb.num_graphs))
+        return (out.x * ct).sum()
+
+    x0 = bb.x.clone().requires_grad_(True)
+    f(x0).backward()
+    analytic = float((x0.grad * vx).sum())
+    with torch.no_grad():
+        numeric = float((f(bb.x + 1e-2 * vx) - f(bb.x - 1e-2 * vx)) / 2e-2)
+    assert abs(numeric - analytic) <= 3e-2 * max(1.0, abs(analytic)), (numeric, analytic)
 
 
 def test_running_stats_and_eval_after_train():

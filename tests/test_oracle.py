@@ -35,7 +35,7 @@ def test_oracle_fp32_close_to_golden(name):
 @pytest.mark.skipif(find_reference_layer_dir() is None, reason="reference layer files not present")
 @pytest.mark.parametrize("local,glob", [("CustomGatedGCN", "Transformer"), ("GINE", "Transformer"),
                                         ("CustomGatedGCN", "Performer"), ("None", "Transformer"),
-                                        ("GINE", "None")])
+                                        ("GINE", "None"), ("GCN", "Transformer"), ("GCN", "None")])
 def test_oracle_equals_reference_live(local, glob):
     ref = load_reference()
     torch.manual_seed(3)
@@ -57,6 +57,31 @@ def test_oracle_equals_reference_live(local, glob):
     for n, p in R.named_parameters():
         if p.grad is not None:
             assert (p.grad - po[n].grad).abs().max() < 1e-9, n
+
+
+def test_gcn_restatements_agree_with_self_loops_and_isolated_nodes():
+    """GCNConv is third-party (PyG 2.2): the shim's message-passing restatement (gcn_norm +
+    add_remaining_self_loops + propagate) and the oracle's dense one must agree, including on graphs with
+    explicit self-loop edges (replaced by the single unit loop), duplicate edges and isolated nodes."""
+    from oracle.gps_oracle import OracleGCN
+    from oracle.ref_shim import _GCNConv
+    torch.manual_seed(0)
+    N, d = 9, 8
+    ei = torch.tensor([[0, 1, 1, 2, 2, 3, 3, 3, 5, 6, 6, 0], [1, 0, 1, 2, 3, 2, 3, 4, 5, 7, 7, 1]])  # loops at 1,2,3,5; dup 6->7, 0->1
+    A, B = _GCNConv(d, d).double(), OracleGCN(d).double()
+    with torch.no_grad():
+        A.bias.uniform_(-1, 1)
+    B.load_state_dict(A.state_dict(), strict=True)
+    x1 = torch.randn(N, d, dtype=torch.float64, requires_grad=True)
+    x2 = x1.detach().clone().requires_grad_(True)
+    y1, y2 = A(x1, ei), B(x2, ei)
+    assert (y1 - y2).abs().max() < 1e-12
+    (y1 ** 2).sum().backward()
+    (y2 ** 2).sum().backward()
+    assert (x1.grad - x2.grad).abs().max() < 1e-12
+    assert (A.lin.weight.grad - B.lin.weight.grad).abs().max() < 1e-12
+    # node 8 is isolated: deg = 1 -> h = x W^T + b
+    assert (y2[8] - (B.lin(x2[8]) + B.bias)).abs().max() < 1e-12
 
 
 def test_parameter_count_kats():
