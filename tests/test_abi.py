@@ -68,3 +68,39 @@ def test_cpu_tensors_fail_loudly():
     b = graphgps_b200.make_batch("zinc-gatedgcn", dim=32, num_graphs=2)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         layer(b)
+
+
+def test_graphgym_glue_rebinds_and_registers(monkeypatch):
+    """rebinding gps_model.GPSLayer, and @register_layer-style registration driven by cfg.gt."""
+    import sys
+    import types
+    from graphgps_b200 import graphgym
+
+    gm = types.ModuleType("graphgps.network.gps_model")
+    gm.GPSLayer = object
+    assert graphgym.install(gm) is object and gm.GPSLayer is graphgps_b200.GPSLayer
+
+    registry = {}
+
+    def register_layer(key, module=None):
+        if key in registry:
+            raise KeyError(key)
+        registry[key] = module
+        return module
+
+    ns = types.SimpleNamespace
+    cfg = ns(gt=ns(layer_type="GINE+Transformer", n_heads=4, dropout=0.1, attn_dropout=0.2, layer_norm=False,
+                   batch_norm=True), gnn=ns(act="gelu"))
+    for name, attrs in (("torch_geometric", {}), ("torch_geometric.graphgym", {}),
+                        ("torch_geometric.graphgym.register", {"register_layer": register_layer}),
+                        ("torch_geometric.graphgym.config", {"cfg": cfg})):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        monkeypatch.setitem(sys.modules, name, m)
+    cls = graphgym.register("gpslayer_b200")
+    assert registry["gpslayer_b200"] is cls
+    layer = cls(ns(dim_out=32))
+    assert (layer.dim_h, layer.local_gnn_type, layer.global_model_type, layer.num_heads) == (32, "GINE", "Transformer", 4)
+    assert layer.act == "gelu" and layer.dropout == 0.1 and layer.attn_dropout == 0.2
+    with pytest.raises(KeyError):
+        graphgym.register("gpslayer_b200")
