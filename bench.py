@@ -476,11 +476,74 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e_ms_total = float(t.item())
 
+    roof = roofline_probe(lib, layer, dev_batches[0], spec, heads, args) if rank == 0 else None
+
+    # ---------------- the model's layer stack (gps_model.py:100,105-108): L GPSLayers back to back, fwd+bwd, as
+    # ONE captured CUDA graph over a resident batch (graph structure shared by all layers).  Measured last and
+    # guarded, so a failure here can only drop this extra key.
+    stack = None
+    if world == 1 and args.graph and spec.layers > 1:
+        try:
+            torch.manual_seed(1)
+            layers = [layer] + [graphgps_b200.GPSLayer(spec.dim, local, glob, heads, dropout=drop, attn_dropout=adrop,
+                                                       precision=args.precision).to(dev).train()
+                                for _ in range(spec.layers - 1)]
+            sparams = [p for l in layers for p in l.parameters()]
+
+            def stack_step(i):
+                b = dev_batches[i]
+                bb = graphgps_b200.GraphBatch(x=b.x.detach().requires_grad_(True), edge_index=b.edge_index,
+                                              edge_attr=b.edge_attr.detach().requires_grad_(True), batch=b.batch,
+                                              num_graphs=b.num_graphs)
+                bb.__dict__["_gps_b200_graph"] = b.__dict__["_gps_b200_graph"]
+                for p in sparams:
+                    p.grad = None
+                out = bb
+                for l in layers:
+                    out = l(out)
+                if gated:
+                    torch.autograd.backward([out.x, out.edge_attr], [cts[i][0], cts[i][1]])
+                else:
+                    torch.autograd.backward([out.x], [cts[i][0]])
+
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(2):
+                    stack_step(i)
+                    stack_step(i)
+            torch.cuda.current_stream().wait_stream(side)
+            sgraphs = []
+            for i in range(2):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    stack_step(i)
+                sgraphs.append(g)
+            for i in range(4):
+                sgraphs[i % 2].replay()
+            torch.cuda.synchronize()
+            se = []
+            nst = min(args.steps, 20)
+            for i in range(nst):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                sgraphs[i % 2].replay()
+                e1.record()
+                se.append((e0, e1))
+            torch.cuda.synchronize()
+            sms = sum(a.elapsed_time(b) for a, b in se) / nst
+            stack = {"layers": spec.layers, "measured": True, "ms_per_step": sms,
+                     "graphs_per_s": spec.num_graphs / (sms * 1e-3),
+                     "how": f"{spec.layers} GPSLayers fwd+bwd in one captured CUDA graph, batch resident, L2 flushed "
+                            f"between steps, {nst} steps"}
+        except Exception as e:   # noqa: BLE001 - the headline numbers above must survive
+            stack = {"layers": spec.layers, "measured": False, "error": repr(e)[:200]}
+
     if rank == 0:
         B = spec.num_graphs
         value = B * world * args.steps / (ms_total * 1e-3)
         e2e_value = B * world * args.steps / (e_ms_total * 1e-3)
-        roof = roofline_probe(lib, layer, dev_batches[0], spec, heads, args)
         ref_layer, kind = cpu_reference_layer(spec, local, glob, heads, drop, adrop)
         cores = pick_cpu_threads(ref_layer, cpu_batches, local)
         ct = time_cpu(ref_layer, cpu_batches, 8, 2, local)
@@ -503,7 +566,9 @@ def run_ours(args):
             "cpu_baseline": {"value": cpu_value, "unit": "graphs/s", "cores": cores, "kind": kind,
                              "sample": f"{len(ct)} steps of one {B}-graph batch fwd+bwd (same workload), "
                                        f"torch fp32, {cores} threads (fastest of 4..64 on a {os.cpu_count()}-core host)"},
-            "stack": {"layers": spec.layers, "graphs_per_s": value / spec.layers},
+            "stack": stack if stack and stack.get("measured") else dict(
+                stack or {}, layers=spec.layers, measured=False, graphs_per_s=value / spec.layers,
+                how="single-layer value / L (not measured as a stack)"),
         }
         print(json.dumps(out), flush=True)
     if world > 1:
