@@ -217,7 +217,7 @@ struct OpBnBwdApply {
   static constexpr int NS = 0;
   const float* g; int64_t ldg; const float* z; int64_t ldz; int64_t d;
   BnView bn; int act; DropCfg drop; const double* sums; float inv_n;
-  float* out; int64_t ldo; float* grad_gamma; float* grad_beta;
+  float* out; int64_t ldo; float* grad_gamma; float* grad_beta; int accumulate;
   BnRegs reg;
   float4 m1, m2, gs;  // S1/n, S2/n, gamma*invstd
   float4 s1raw, s2raw;
@@ -242,8 +242,8 @@ struct OpBnBwdApply {
   __device__ double* stat_ptr(int) { return nullptr; }
   __device__ void finish(int c4, int ry) {
     if (blockIdx.x == 0 && ry == 0) {
-      if (grad_gamma) st4(grad_gamma + c4 * 4, s2raw);
-      if (grad_beta) st4(grad_beta + c4 * 4, s1raw);
+      if (grad_gamma) st4(grad_gamma + c4 * 4, accumulate ? f4add(ld4(grad_gamma + c4 * 4), s2raw) : s2raw);
+      if (grad_beta) st4(grad_beta + c4 * 4, accumulate ? f4add(ld4(grad_beta + c4 * 4), s1raw) : s1raw);
     }
   }
 };
@@ -321,13 +321,13 @@ int bn_bwd_reduce(const float* g, int64_t ldg, const float* z, int64_t ldz, int6
 
 int bn_bwd_apply(const float* g, int64_t ldg, const float* z, int64_t ldz, int64_t rows, int64_t d, BnView bn,
                  int act, DropCfg drop, const double* sums, float* out, int64_t ldo, float* grad_gamma,
-                 float* grad_beta, cudaStream_t stream) {
+                 float* grad_beta, cudaStream_t stream, bool accumulate) {
   OpBnBwdApply op{g, ldg, z, ldz, d, bn, act, drop, sums, 1.f / (float)(rows > 0 ? rows : 1),
-                  out, ldo, grad_gamma, grad_beta};
+                  out, ldo, grad_gamma, grad_beta, accumulate ? 1 : 0};
   if (rows == 0) {
     // no rows: gradients of gamma/beta are zero
-    if (grad_gamma) GPS_CUDA(cudaMemsetAsync(grad_gamma, 0, d * sizeof(float), stream));
-    if (grad_beta) GPS_CUDA(cudaMemsetAsync(grad_beta, 0, d * sizeof(float), stream));
+    if (grad_gamma && !accumulate) GPS_CUDA(cudaMemsetAsync(grad_gamma, 0, d * sizeof(float), stream));
+    if (grad_beta && !accumulate) GPS_CUDA(cudaMemsetAsync(grad_beta, 0, d * sizeof(float), stream));
     return GPS_OK;
   }
   return launch_rowwise(op, rows, d, stream);

@@ -23,6 +23,8 @@ struct GemmParams {
   int mask_is_post = 0;                    // relu only: mask_src holds the post-activation value
   float p_drop = 0.f; uint64_t seed = 0, offset = 0; int site = 0;    // dropout on the result
   const unsigned long long* offset_dev = nullptr;                     // optional device-resident addend to offset
+  float p_drop2 = 0.f; int site2 = 0;      // optional inner dropout applied before the one above (Performer: attn_dropout
+                                           // on to_out(O) inside SelfAttention, then GPSLayer.dropout_attn)
   const float* R1 = nullptr; int ldr1 = 0;
   const float* R2 = nullptr; int ldr2 = 0;
   double* stats = nullptr;                 // [2][N] column sum / sum of squares of the stored C

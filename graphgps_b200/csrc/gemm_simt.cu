@@ -147,6 +147,11 @@ __global__ void __launch_bounds__(NT) k_gemm_simt(GemmParams p, int kchunk, bool
           v[j] *= p.mask_is_post ? (ms > 0.f ? 1.f : 0.f) : act_bwd_rt(p.mask_act, ms);
         }
     }
+    if (p.p_drop2 > 0.f) {
+      float4 sc = dropout_scale4(p.p_drop2, p.seed, p.offset + (p.offset_dev ? *p.offset_dev : 0ull), p.site2,
+                                 ((uint64_t)gm * (uint64_t)p.N + gn) >> 2);
+      v[0] *= sc.x; v[1] *= sc.y; v[2] *= sc.z; v[3] *= sc.w;
+    }
     if (p.p_drop > 0.f) {
       // gn is a multiple of 4 and ldc-independent: flat index over a dense [M, N] grid
       float4 sc = dropout_scale4(p.p_drop, p.seed, p.offset + (p.offset_dev ? *p.offset_dev : 0ull), p.site,
@@ -205,10 +210,10 @@ int gemm_simt(const GemmParams& p, cudaStream_t stream) {
   if (p.M == 0 || p.N == 0) return GPS_OK;
   GPS_REQUIRE(p.splitk >= 1, GPS_ERR_ARG, "gemm: splitk < 1");
   if (p.splitk > 1)
-    GPS_REQUIRE(!p.bias && p.act < 0 && !p.mask_src && !p.stats && !p.C_pre && p.p_drop == 0.f, GPS_ERR_ARG,
+    GPS_REQUIRE(!p.bias && p.act < 0 && !p.mask_src && !p.stats && !p.C_pre && p.p_drop == 0.f && p.p_drop2 == 0.f, GPS_ERR_ARG,
                 "gemm: split-K supports the plain product (+ residuals) only");
   GPS_REQUIRE(p.colsum_a == nullptr || p.ta == 1, GPS_ERR_ARG, "gemm: colsum_a needs ta == 1");
-  GPS_REQUIRE(p.p_drop == 0.f || (p.N % 4 == 0), GPS_ERR_ARG, "gemm: dropout epilogue needs N %% 4 == 0");
+  GPS_REQUIRE((p.p_drop == 0.f && p.p_drop2 == 0.f) || (p.N % 4 == 0), GPS_ERR_ARG, "gemm: dropout epilogue needs N %% 4 == 0");
   int splitk = p.splitk;
   int kchunk = (int)round_up(ceil_div(p.K > 0 ? p.K : 1, splitk), BK);
   splitk = (int)ceil_div(p.K > 0 ? p.K : 1, kchunk);

@@ -415,6 +415,11 @@ __global__ void __launch_bounds__(kThreads, NBC == 2 ? 2 : 1) k_gemm_tc(const Tc
 #pragma unroll
             for (int e = 0; e < 4; ++e) w[e] *= p.mask_is_post ? (mv[e] > 0.f ? 1.f : 0.f) : act_bwd_rt(p.mask_act, mv[e]);
           }
+          if (ok && p.p_drop2 > 0.f) {
+            float4 sc = dropout_scale4(p.p_drop2, p.seed, p.offset + (p.offset_dev ? *p.offset_dev : 0ull), p.site2,
+                                     ((uint64_t)row * (uint64_t)p.N + col) >> 2);
+            w[0] *= sc.x; w[1] *= sc.y; w[2] *= sc.z; w[3] *= sc.w;
+          }
           if (ok && p.p_drop > 0.f) {
             float4 sc = dropout_scale4(p.p_drop, p.seed, p.offset + (p.offset_dev ? *p.offset_dev : 0ull), p.site,
                                      ((uint64_t)row * (uint64_t)p.N + col) >> 2);
@@ -538,7 +543,7 @@ int gemm_tc(const GemmParams& p, cudaStream_t stream) {
     return GPS_ERR_UNSUPPORTED;
   // lean producer loop: whole 8-element chunks are either inside or outside the operand
   if ((!p.ta && p.K % 8) || (!p.tb && p.K % 8) || (p.ta && p.M % 8) || (p.tb && p.N % 8)) return GPS_ERR_UNSUPPORTED;
-  if (p.splitk > 1 && (p.bias || p.act >= 0 || p.mask_src || p.stats || p.C_pre || p.p_drop != 0.f)) {
+  if (p.splitk > 1 && (p.bias || p.act >= 0 || p.mask_src || p.stats || p.C_pre || p.p_drop != 0.f || p.p_drop2 != 0.f)) {
     set_error("gemm: split-K supports the plain product (+ residuals) only");
     return GPS_ERR_ARG;
   }

@@ -49,7 +49,7 @@ int bn_bwd_reduce(const float* g, int64_t ldg, const float* z, int64_t ldz, int6
 // out = gamma*invstd*(g' - S1/n - zhat*S2/n) (+ add); also writes grad_gamma = S2, grad_beta = S1
 int bn_bwd_apply(const float* g, int64_t ldg, const float* z, int64_t ldz, int64_t rows, int64_t d, BnView bn,
                  int act, DropCfg drop, const double* sums, float* out, int64_t ldo, float* grad_gamma,
-                 float* grad_beta, cudaStream_t stream);
+                 float* grad_beta, cudaStream_t stream, bool accumulate = false);
 // out = a + b (+ c)   row-wise with independent leading dimensions
 int add3(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, float* out,
          int64_t ldo, int64_t rows, int64_t d, cudaStream_t stream);

@@ -144,16 +144,17 @@ __global__ void k_pack(PackDesc pd, float* __restrict__ Wcat, float* __restrict_
   for (int c = threadIdx.x * 4; c < pd.d; c += blockDim.x * 4) st4(dst + c, ld4(src + c));
   if (threadIdx.x == 0) bcat[r] = pd.seg[s].b ? pd.seg[s].b[r - row0] : 0.f;
 }
-__global__ void k_unpack(PackDesc pd, const float* __restrict__ gWcat, const float* __restrict__ gbcat) {
+__global__ void k_unpack(PackDesc pd, const float* __restrict__ gWcat, const float* __restrict__ gbcat, int accumulate) {
   const int r = blockIdx.x;
   int row0 = 0, s = 0;
   while (s < pd.nseg - 1 && r >= row0 + pd.seg[s].rows) row0 += pd.seg[s++].rows;
   if (pd.seg[s].gw) {
     float* dst = pd.seg[s].gw + (int64_t)(r - row0) * pd.d;
     const float* src = gWcat + (int64_t)r * pd.d;
-    for (int c = threadIdx.x * 4; c < pd.d; c += blockDim.x * 4) st4(dst + c, ld4(src + c));
+    for (int c = threadIdx.x * 4; c < pd.d; c += blockDim.x * 4)
+      st4(dst + c, accumulate ? f4add(ld4(dst + c), ld4(src + c)) : ld4(src + c));
   }
-  if (threadIdx.x == 0 && pd.seg[s].gb) pd.seg[s].gb[r - row0] = gbcat[r];
+  if (threadIdx.x == 0 && pd.seg[s].gb) pd.seg[s].gb[r - row0] = (accumulate ? pd.seg[s].gb[r - row0] : 0.f) + gbcat[r];
 }
 
 enum { BN_X = 0, BN_E = 1, BN_L = 2, BN_A = 3, BN_2 = 4, BN_COUNT = 5 };
@@ -312,8 +313,8 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
   P->g_hid = Bk.alloc<float>(N * 2 * d);
   P->g_s = Bk.alloc<float>(N * d);
   P->g_tmp = Bk.alloc<float>(N * d);
-  if (a->dropout > 0.f) {   // separate dropout temporaries: side-stream weight gradients still read the earlier ones
-    P->g_tmp2 = Bk.alloc<float>(N * d);
+  if (a->dropout > 0.f || (P->perf && a->attn_dropout > 0.f)) {   // separate dropout temporaries: side-stream weight
+    P->g_tmp2 = Bk.alloc<float>(N * d);                            // gradients still read the earlier ones
     P->g_tmp3 = Bk.alloc<float>(N * d);
   }
   if (P->gated || P->gine || P->gcn) P->g_xloc = Bk.alloc<float>(N * d);
@@ -454,6 +455,9 @@ static int check_params(const GpsLayerArgs* a, const Plan& P) {
 // set per call from GpsLayerArgs.reserved0 bit 0: the caller already zeroed every parameter-gradient buffer
 // (one multi-tensor fill instead of a memset per weight and bias)
 static thread_local bool g_grads_prezeroed = false;
+// GpsLayerArgs.reserved0 bit 1: parameter gradients are ADDED to the caller's buffers (torch's .grad accumulation
+// semantics on a static gradient bucket: graphgps_b200/dp.py); implies bit 0
+static thread_local bool g_grads_accumulate = false;
 
 static int splitk_for(int64_t rows, int64_t out = 304, int64_t in = 304) {
   // Weight gradients reduce over `rows` (nodes/edges) into a small [out, in] tile grid: split the reduction so
@@ -685,7 +689,10 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.M = (int)N; g.N = (int)d; g.K = (int)inner;
     g.A = P.O; g.lda = (int)inner; g.B = a->attn_out.weight; g.ldb = (int)inner; g.C = P.hA; g.ldc = (int)d;
     g.bias = a->attn_out.bias; g.R1 = a->x; g.ldr1 = (int)d; g.stats = stats(BN_A);
+    // SelfAttention ends with dropout(p = attn_dropout) on to_out(O) (performer_layer.py:501-503, built with
+    // dropout=self.attn_dropout at gps_layer.py:112-114); GPSLayer.dropout_attn (p = dropout) follows (:212)
     g.p_drop = pd > 0.f ? pd : 0.f; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_ATTN_OUT;
+    g.p_drop2 = pa; g.site2 = GPS_SITE_PERF_OUT;
     g.offset_dev = (const unsigned long long*)a->offset_dev;
     g.precision = a->precision;
     GPS_TRY(gemm(g, sg));
@@ -730,7 +737,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
 // =================================================================================== backward
 // out = a * dropout_scale(site)  (only launched when p > 0)
 static int dropmul(const float* src, float* dst, int64_t rows, int64_t d, const Plan& P, const GpsLayerArgs* a,
-                   int site, cudaStream_t st);
+                   int site, cudaStream_t st, float p2 = 0.f, int site2 = 0);
 
 static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   Plan P;
@@ -740,7 +747,8 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
               (long long)a->workspace_bytes, (long long)P.bwd_bytes);
   GPS_TRY(check_params(a, P));
   GPS_REQUIRE(a->training, GPS_ERR_UNSUPPORTED, "backward is implemented for training mode (batch statistics)");
-  g_grads_prezeroed = (a->reserved0 & 1) != 0;
+  g_grads_accumulate = (a->reserved0 & 2) != 0;
+  g_grads_prezeroed = (a->reserved0 & 1) != 0 || g_grads_accumulate;
   GPS_REQUIRE(a->grad_x_out && a->grad_x, GPS_ERR_ARG, "grad_x_out / grad_x are required");
   const int64_t N = P.N, E = P.E, d = P.d;
   const int act = a->act, prec = a->precision;
@@ -794,11 +802,13 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     if (a->grad_edge_out && E > 0) {
       GPS_TRY(bn_bwd_reduce(a->grad_edge_out, d, P.ehat, d, E, d, ve, act, drop(GPS_SITE_GCN_E), sums(BN_E), se));
       GPS_TRY(bn_bwd_apply(a->grad_edge_out, d, P.ehat, d, E, d, ve, act, drop(GPS_SITE_GCN_E), sums(BN_E), P.g_e, d,
-                           a->bn_edge_e.grad_weight, a->bn_edge_e.grad_bias, se));
+                           a->bn_edge_e.grad_weight, a->bn_edge_e.grad_bias, se, g_grads_accumulate));
     } else {
       if (E > 0) GPS_CUDA(cudaMemsetAsync(P.g_e, 0, (size_t)(E * d) * sizeof(float), se));
-      if (a->bn_edge_e.grad_weight) GPS_CUDA(cudaMemsetAsync(a->bn_edge_e.grad_weight, 0, d * sizeof(float), se));
-      if (a->bn_edge_e.grad_bias) GPS_CUDA(cudaMemsetAsync(a->bn_edge_e.grad_bias, 0, d * sizeof(float), se));
+      if (a->bn_edge_e.grad_weight && !g_grads_prezeroed)
+        GPS_CUDA(cudaMemsetAsync(a->bn_edge_e.grad_weight, 0, d * sizeof(float), se));
+      if (a->bn_edge_e.grad_bias && !g_grads_prezeroed)
+        GPS_CUDA(cudaMemsetAsync(a->bn_edge_e.grad_bias, 0, d * sizeof(float), se));
     }
     return GPS_OK;
   };
@@ -808,7 +818,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   BnView v2 = bn_view(P, BN_2, a->norm2);
   GPS_TRY(bn_bwd_reduce(a->grad_x_out, d, P.t, d, N, d, v2, -1, nodrop, sums(BN_2), st));
   GPS_TRY(bn_bwd_apply(a->grad_x_out, d, P.t, d, N, d, v2, -1, nodrop, sums(BN_2), P.g_t, d, a->norm2.grad_weight,
-                       a->norm2.grad_bias, st));
+                       a->norm2.grad_bias, st, g_grads_accumulate));
 
   // ---- FFN (gps_layer.py:253-257)
   const float* g_ff2 = P.g_t;  // gradient at the output of ff_linear2 (after ff_dropout2)
@@ -843,14 +853,14 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     BnView v = bn_view(P, BN_L, a->norm1_local);
     GPS_TRY(bn_bwd_reduce(P.g_s, d, P.xloc, d, N, d, v, -1, nodrop, sums(BN_L), st));
     GPS_TRY(bn_bwd_apply(P.g_s, d, P.xloc, d, N, d, v, -1, nodrop, sums(BN_L), P.g_xloc, d,
-                         a->norm1_local.grad_weight, a->norm1_local.grad_bias, st));
+                         a->norm1_local.grad_weight, a->norm1_local.grad_bias, st, g_grads_accumulate));
   }
   if (two_branches && sd) GPS_TRY(sd->order(st, sa));   // attention-branch backward runs next to the local-model backward
   if (P.attn) {
     BnView v = bn_view(P, BN_A, a->norm1_attn);
     GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), sa));
     GPS_TRY(bn_bwd_apply(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), P.g_hA, d, a->norm1_attn.grad_weight,
-                         a->norm1_attn.grad_bias, sa));
+                         a->norm1_attn.grad_bias, sa, g_grads_accumulate));
     // hA = x + drop(O Wo^T + bo)
     const float* g_ao = P.g_hA;
     if (pd > 0.f) {
@@ -876,10 +886,10 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     BnView v = bn_view(P, BN_A, a->norm1_attn);
     GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), sa));
     GPS_TRY(bn_bwd_apply(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), P.g_hA, d, a->norm1_attn.grad_weight,
-                         a->norm1_attn.grad_bias, sa));
-    const float* g_ao = P.g_hA;   // hA = x + drop(to_out(O))
-    if (pd > 0.f) {
-      GPS_TRY(dropmul(P.g_hA, P.g_tmp2, N, d, P, a, GPS_SITE_ATTN_OUT, sa));
+                         a->norm1_attn.grad_bias, sa, g_grads_accumulate));
+    const float* g_ao = P.g_hA;   // hA = x + drop_pd(drop_pa(to_out(O)))
+    if (pd > 0.f || pa > 0.f) {
+      GPS_TRY(dropmul(P.g_hA, P.g_tmp2, N, d, P, a, GPS_SITE_ATTN_OUT, sa, pa, GPS_SITE_PERF_OUT));
       g_ao = P.g_tmp2;
     }
     GemmParams g;  // g_O = g_ao Wout   [N, inner]
@@ -929,7 +939,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     BnView vx = bn_view(P, BN_X, a->bn_node_x);
     GPS_TRY(bn_bwd_reduce(P.g_xloc, d, P.xt, d, N, d, vx, act, drop(GPS_SITE_GCN_X), sums(BN_X), st));
     GPS_TRY(bn_bwd_apply(P.g_xloc, d, P.xt, d, N, d, vx, act, drop(GPS_SITE_GCN_X), sums(BN_X), P.gY1, P.Wy,
-                         a->bn_node_x.grad_weight, a->bn_node_x.grad_bias, st));
+                         a->bn_node_x.grad_weight, a->bn_node_x.grad_bias, st, g_grads_accumulate));
     if (!early_edge) GPS_TRY(edge_bn_bwd());
     if (se != st) GPS_TRY(sd->order(se, st));
     // message/aggregate backward
@@ -1008,7 +1018,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(wfork(st));
     GPS_TRY(wcat_wgrad(wl, wg));
     PackDesc pdsc = pack_desc(a, P);
-    k_unpack<<<(unsigned)pdsc.total_rows, 128, 0, s2>>>(pdsc, P.gWcat, P.gbcat);
+    k_unpack<<<(unsigned)pdsc.total_rows, 128, 0, s2>>>(pdsc, P.gWcat, P.gbcat, g_grads_accumulate ? 1 : 0);
     GPS_LAUNCH_CHECK();
     GemmParams g;   // g_x += g_hA + gY1[:, wl:] Wcat[wl:]  (accumulated onto the first share)
     g.M = (int)N; g.N = (int)d; g.K = (int)wg;
@@ -1030,7 +1040,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     w.colsum_a = P.gbcat; w.precision = prec;
     if (N > 0) GPS_TRY(gemm(w, s2));
     PackDesc pdsc = pack_desc(a, P);
-    k_unpack<<<(unsigned)pdsc.total_rows, 128, 0, s2>>>(pdsc, P.gWcat, P.gbcat);
+    k_unpack<<<(unsigned)pdsc.total_rows, 128, 0, s2>>>(pdsc, P.gWcat, P.gbcat, g_grads_accumulate ? 1 : 0);
     GPS_LAUNCH_CHECK();
     GemmParams g;
     g.M = (int)N; g.N = (int)d; g.K = (int)P.Wy;
@@ -1057,11 +1067,14 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
 // dedicated tiny kernel keeps it explicit.
 namespace {
 __global__ void k_dropmul(const float* __restrict__ src, float* __restrict__ dst, int64_t n4, int64_t c4n, float p,
-                          uint64_t seed, uint64_t offset, int site, const unsigned long long* offset_dev) {
+                          uint64_t seed, uint64_t offset, int site, const unsigned long long* offset_dev, float p2,
+                          int site2) {
   if (offset_dev) offset += *offset_dev;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = ld4(src + i * 4);
-    st4(dst + i * 4, f4mul(v, dropout_scale4(p, seed, offset, site, (uint64_t)i)));
+    if (p > 0.f) v = f4mul(v, dropout_scale4(p, seed, offset, site, (uint64_t)i));
+    if (p2 > 0.f) v = f4mul(v, dropout_scale4(p2, seed, offset, site2, (uint64_t)i));
+    st4(dst + i * 4, v);
   }
 }
 __global__ void k_dropmask(float* __restrict__ dst, int64_t n4, float p, uint64_t seed, uint64_t offset, int site) {
@@ -1074,12 +1087,13 @@ __global__ void k_dropmask(float* __restrict__ dst, int64_t n4, float p, uint64_
 }  // namespace
 
 static int dropmul(const float* src, float* dst, int64_t rows, int64_t d, const Plan&, const GpsLayerArgs* a, int site,
-                   cudaStream_t st) {
+                   cudaStream_t st, float p2, int site2) {
   int64_t n4 = rows * d / 4;
   if (n4 == 0) return GPS_OK;
   k_dropmul<<<(unsigned)std::min<int64_t>(ceil_div(n4, 256), kNumSMs * 8), 256, 0, st>>>(src, dst, n4, d / 4, a->dropout,
                                                                                         a->seed, a->offset, site,
-                                                                                        (const unsigned long long*)a->offset_dev);
+                                                                                        (const unsigned long long*)a->offset_dev,
+                                                                                        p2, site2);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }

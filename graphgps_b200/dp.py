@@ -2,14 +2,27 @@
 
 Graph mini-batches are independent units: every rank runs its own 256-graph batch through the full
 layer with per-replica BatchNorm statistics (the reference has no SyncBN), and the only exchange is
-one all-reduce (mean) of the parameter gradients per step over NCCL/NVLink.  The gradients of a
-layer (13d^2+22d floats, 4.8 MB at d=304) are flattened into one bucket so the collective is a
-single launch-latency-bound call.  The reference itself has no distributed code at all.
+the all-reduce (mean) of the parameter gradients, once per optimiser step over NCCL/NVLink
+(the reference's hook would sit between `loss.backward()` and `optimizer.step()`,
+graphgps/train/custom_train.py:32-38; the reference itself has no distributed code at all).
+
+`GradBucket` is the product path: ONE static flat fp32 buffer holds the gradients of a set of layers;
+every parameter's `.grad` is a view of it and `gps_layer_backward` adds its gradients straight into
+those views (GpsLayerArgs.reserved0 bit 1).  CUDA-graph replays, the optimiser and the collective
+therefore all see the same memory: the all-reduce runs in place on the bucket (ReduceOp.AVG on NCCL,
+no copy-in / scale / copy-out) and can be captured in the same CUDA graph as the step.  Parameters are
+laid out in two contiguous groups per layer - "early" (FFN, attention output projection and the three
+GPSLayer norms, final a few hundred microseconds before the backward pass ends) and "late" (the node/edge
+projections, final only at the very end) - so the early group's collective can be issued on a side stream
+while the rest of the backward pass still runs (`GradBucket.allreduce(overlap=...)`).
 """
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
+
+_EARLY_PREFIXES = ("ff_linear1.", "ff_linear2.", "norm2.", "norm1_local.", "norm1_attn.",
+                   "self_attn.out_proj.", "self_attn.to_out.")
 
 
 def shard_graph_range(num_graphs: int, rank: int, world: int):
@@ -19,8 +32,74 @@ def shard_graph_range(num_graphs: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class GradBucket:
+    """Static flat gradient storage for one or more `graphgps_b200.GPSLayer`s (or any nn.Modules).
+
+    After construction `p.grad` of every parameter is a view of `self.flat`.  Keep them that way:
+    zero with `bucket.zero_()` (or `optimizer.zero_grad(set_to_none=False)`), never `set_to_none=True`.
+    """
+
+    def __init__(self, layers, device=None):
+        self.layers = list(layers)
+        entries = []   # (layer index, early?, name, param)
+        for li, layer in enumerate(self.layers):
+            for n, p in layer.named_parameters():
+                entries.append((li, n.startswith(_EARLY_PREFIXES), n, p))
+        if not entries:
+            raise ValueError("GradBucket: no parameters")
+        device = device or entries[0][3].device
+        # layer-major; inside a layer the early group first.  16-float alignment keeps every view 64-byte aligned.
+        order = sorted(range(len(entries)), key=lambda i: (entries[i][0], not entries[i][1]))
+        offs, off = {}, 0
+        self.segments = []   # (layer, early, begin, end) in element offsets
+        cur = None
+        for i in order:
+            li, early, n, p = entries[i]
+            if cur is None or cur[0] != li or cur[1] != early:
+                if cur is not None:
+                    self.segments.append((cur[0], cur[1], cur[2], off))
+                cur = [li, early, off]
+            offs[i] = off
+            off += (p.numel() + 15) // 16 * 16
+        self.segments.append((cur[0], cur[1], cur[2], off))
+        self.flat = torch.zeros(off, dtype=torch.float32, device=device)
+        for i, (li, early, n, p) in enumerate(entries):
+            if p.dtype != torch.float32 or p.device != self.flat.device:
+                raise TypeError(f"GradBucket: parameter {n} must be float32 on {self.flat.device}")
+            p.grad = self.flat[offs[i]:offs[i] + p.numel()].view_as(p)
+        lo = self.flat.data_ptr()
+        hi = lo + self.flat.numel() * 4
+        for layer in self.layers:
+            layer.__dict__["_grad_bucket"] = (lo, hi)
+
+    def zero_(self):
+        self.flat.zero_()
+        return self
+
+    def segment(self, layer: int, early: bool):
+        for li, e, b, en in self.segments:
+            if li == layer and e == early:
+                return self.flat[b:en]
+        return None
+
+    def allreduce(self, group=None, segments=None):
+        """In-place mean over ranks of the whole bucket (or of the given list of flat slices)."""
+        world = dist.get_world_size(group)
+        if world == 1:
+            return
+        parts = segments if segments is not None else [self.flat]
+        avg = dist.get_backend(group) == "nccl"
+        for t in parts:
+            if avg:
+                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=group)
+            else:   # gloo has no AVG
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+                t.mul_(1.0 / world)
+
+
 def allreduce_gradients(params, bucket=None, group=None):
-    """All-reduce (mean) the .grad of `params` through one flat bucket. Returns the bucket for reuse."""
+    """Generic fallback for parameters whose .grad is NOT bucket-backed: all-reduce (mean) through a flat staging
+    buffer (copy in, reduce, copy out).  Returns the staging buffer for reuse."""
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:
         return bucket

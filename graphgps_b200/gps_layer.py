@@ -46,11 +46,16 @@ def _next_dropout_offset(device):
 
 
 def _workspace(device, nbytes):
-    ws = _workspaces.get(device)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
-        _workspaces[device] = ws
-    return ws
+    """Transient scratch for one C call, one buffer per (device, stream): layers running on different streams never
+    share it, and a buffer is never freed while the process lives (a captured CUDA graph may hold its address) -
+    growth keeps the old ones.  Under stream capture the buffer is allocated from the graph's own pool instead."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    held = _workspaces.setdefault(key, [])
+    if not held or held[-1].numel() < nbytes:
+        held.append(torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device))
+    return held[-1]
 
 
 class _GatedGCNParams(nn.Module):
@@ -175,10 +180,19 @@ class _GPSLayerFn(torch.autograd.Function):
             raise RuntimeError("GPSLayer backward needs training mode (BatchNorm batch statistics)")
         dev = x.device
         named = dict(zip(layer._param_names, params))
-        grads = {n: torch.empty_like(p) for n, p in named.items()}
-        torch._foreach_zero_(list(grads.values()))   # one multi-tensor fill; the library then skips its memsets
-        args = layer._base_args(gs, named, grads)
-        args.reserved0 = 1
+        bucket = layer._bucket_grads(named)
+        if bucket is not None:
+            # static gradient bucket (graphgps_b200.dp.GradBucket): the library ADDS this call's gradients to the
+            # parameters' .grad views in place (torch's accumulation semantics), so CUDA-graph replays and the
+            # gradient all-reduce see the same memory
+            grads = bucket
+            args = layer._base_args(gs, named, grads)
+            args.reserved0 = 3
+        else:
+            grads = {n: torch.empty_like(p) for n, p in named.items()}
+            torch._foreach_zero_(list(grads.values()))   # one multi-tensor fill; the library then skips its memsets
+            args = layer._base_args(gs, named, grads)
+            args.reserved0 = 1
         args.seed, args.offset, args.training = ctx.seed, ctx.offset, 1
         if ctx.snap is not None:
             args.offset_dev = ctx.snap.data_ptr()
@@ -198,7 +212,9 @@ class _GPSLayerFn(torch.autograd.Function):
         args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.gps_layer_backward(C.byref(args), stream), "gps_layer_backward")
-        ctx.saved_buf = None
+        # (ctx.saved_buf stays alive with the autograd node: backward(retain_graph=True) may run again)
+        if bucket is not None:
+            return (None, None, g_x, g_e) + (None,) * len(layer._param_names)
         # parameters the configuration never reads get no gradient (as under autograd in the reference)
         unused = []
         if layer.local_gnn_type == "None":
@@ -292,9 +308,23 @@ class GPSLayer(nn.Module):
         self._grad_numel = sum(self._grad_sizes)
         self._plan_cache = {}
 
+    def _bucket_grads(self, named):
+        """{name: .grad view} when every parameter's .grad is a view of this layer's static bucket, else None."""
+        b = self.__dict__.get("_grad_bucket")
+        if b is None:
+            return None
+        lo, hi = b
+        out = {}
+        for n, p in self.named_parameters():
+            g = p.grad
+            if g is None or not (lo <= g.data_ptr() < hi) or not g.is_contiguous():
+                return None
+            out[n] = g
+        return out
+
     def _plan(self, args, gs):
-        """(saved_bytes, workspace_bytes) for this graph size; gps_layer_plan is pure in (config, N, E)."""
-        key = (gs.N, gs.E)
+        """(saved_bytes, workspace_bytes); gps_layer_plan is pure in (config, N, E, B, training, precision)."""
+        key = (gs.N, gs.E, gs.B, bool(self.training), self.precision, float(self.dropout), float(self.attn_dropout))
         hit = self._plan_cache.get(key)
         if hit is None:
             plan = _lib.GpsLayerPlan()
@@ -317,6 +347,7 @@ class GPSLayer(nn.Module):
                    float(self.dropout), float(self.attn_dropout))
             cached = self.__dict__.get("_args_cache")
             if cached is None or cached[0] != key:
+                self._check_params(named)
                 cached = (key, self._build_args(named, None))
                 self.__dict__["_args_cache"] = cached
             a = _lib.GpsLayerArgs.from_buffer_copy(cached[1])
@@ -327,6 +358,14 @@ class GPSLayer(nn.Module):
         a.offset = _dropout_calls[0] * 4096
         a.graph = gs.desc
         return a
+
+    def _check_params(self, named):
+        """The library reads raw fp32 device pointers: refuse anything else (the reference would cast or raise)."""
+        bufs = {n: b for n, b in self.named_buffers() if b.is_floating_point()}
+        for n, t in list(named.items()) + list(bufs.items()):
+            if t.dtype != torch.float32 or not t.is_cuda or not t.is_contiguous():
+                raise TypeError(f"graphgps_b200.GPSLayer: parameter/buffer '{n}' must be a contiguous float32 CUDA "
+                                f"tensor (got {t.dtype} on {t.device})")
 
     def _build_args(self, named, grads):
         g = grads or {}
@@ -397,6 +436,8 @@ class GPSLayer(nn.Module):
         if self.local_gnn_type in _EDGE_LOCAL:
             if e is None or e.shape[-1] != self.dim_h:
                 raise ValueError("Node and edge feature dimensionalities do not match")
+            if e.dtype != torch.float32 or e.device != x.device:
+                raise TypeError("batch.edge_attr must be float32 on the device of batch.x")
             e = e.contiguous()
         else:
             e = None

@@ -8,6 +8,8 @@ layer: PyG propagate's index_select/scatter bookkeeping (graphgps/layer/gatedgcn
 from __future__ import annotations
 
 import ctypes as C
+import os
+import weakref
 
 import torch
 
@@ -27,6 +29,11 @@ class GraphStructure:
         if edge_index.dim() != 2 or edge_index.shape[0] != 2:
             raise ValueError("edge_index must have shape [2, E]")
         lib = _lib.load()
+        if os.environ.get("GPS_B200_CHECK", "0") == "1" and edge_index.numel():
+            # debug switch: the CSR build scatters through edge_index unchecked (one host sync when enabled)
+            lo, hi = int(edge_index.min()), int(edge_index.max())
+            if lo < 0 or hi >= int(batch.shape[0]):
+                raise IndexError(f"edge_index values [{lo}, {hi}] out of range for {int(batch.shape[0])} nodes")
         self.N = int(batch.shape[0])
         self.E = int(edge_index.shape[1])
         self.B = int(num_graphs)
@@ -74,16 +81,44 @@ def _num_graphs(batch_obj) -> int:
     return int(b[-1].item()) + 1 if b.numel() else 0
 
 
+_side_cache = weakref.WeakKeyDictionary()   # batch objects whose attribute protocol does not round-trip
+
+
+def _cache_get(batch_obj):
+    # PyG Data/Batch route setattr/getattr through their storage object (underscore names included), so read the
+    # way we write; a plain __dict__ lookup would never hit there and the CSR build would rerun in every layer
+    try:
+        hit = getattr(batch_obj, _CACHE_ATTR, None)
+    except Exception:
+        hit = None
+    if hit is None:
+        try:
+            hit = _side_cache.get(batch_obj)
+        except TypeError:
+            hit = None
+    return hit if isinstance(hit, GraphStructure) else None
+
+
+def _cache_put(batch_obj, gs):
+    try:
+        setattr(batch_obj, _CACHE_ATTR, gs)
+        if getattr(batch_obj, _CACHE_ATTR, None) is gs:
+            return
+    except Exception:
+        pass
+    try:
+        _side_cache[batch_obj] = gs
+    except TypeError:  # not weak-referenceable: still works, just rebuilds per layer
+        pass
+
+
 def graph_of(batch_obj) -> GraphStructure:
     """Returns the cached structure of `batch_obj`, building it on first use."""
     ei, bv = batch_obj.edge_index, batch_obj.batch
-    cached = batch_obj.__dict__.get(_CACHE_ATTR) if hasattr(batch_obj, "__dict__") else None
+    cached = _cache_get(batch_obj)
     key = (ei.data_ptr(), bv.data_ptr(), int(bv.shape[0]), int(ei.shape[1]), ei._version, bv._version)
     if cached is not None and cached.key == key:
         return cached
     gs = GraphStructure(ei, bv, _num_graphs(batch_obj))
-    try:
-        setattr(batch_obj, _CACHE_ATTR, gs)
-    except Exception:  # objects that refuse new attributes still work, just rebuild per layer
-        pass
+    _cache_put(batch_obj, gs)
     return gs

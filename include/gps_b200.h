@@ -116,7 +116,7 @@ typedef struct {
   int32_t act;               /* GPS_ACT_*                                           */
   int32_t training;          /* 1: batch statistics + dropout; 0: running stats     */
   int32_t precision;         /* GPS_PREC_*                                          */
-  int32_t reserved0;         /* flags; bit 0 (backward): parameter-gradient buffers are already zero  */
+  int32_t reserved0;         /* flags; bit 0 (backward): parameter-gradient buffers are already zero; bit 1: gradients are added to the buffers */
   float dropout;             /* cfg.gt.dropout       (gps_layer.py:92-96,139-140,152-153) */
   float attn_dropout;        /* cfg.gt.attn_dropout  (gps_layer.py:105-106,112-114)       */
   uint64_t seed;             /* Philox key for this call's dropout masks            */

@@ -104,3 +104,34 @@ def test_graphgym_glue_rebinds_and_registers(monkeypatch):
     assert layer.act == "gelu" and layer.dropout == 0.1 and layer.attn_dropout == 0.2
     with pytest.raises(KeyError):
         graphgym.register("gpslayer_b200")
+
+
+def test_graph_cache_round_trips_on_storage_backed_batches():
+    """PyG Data/Batch keep attributes (underscore names included) in a storage object, not in __dict__: the cache
+    must be read the way it is written.  No GPU needed: the cached object is only compared by identity."""
+    from graphgps_b200 import graph as G
+
+    class StoreBacked:                      # mimics torch_geometric.data.Data attribute routing
+        def __init__(self):
+            object.__setattr__(self, "_store", {})
+
+        def __setattr__(self, k, v):
+            self._store[k] = v
+
+        def __getattr__(self, k):
+            try:
+                return object.__getattribute__(self, "_store")[k]
+            except KeyError:
+                raise AttributeError(k)
+
+    class Frozen:                           # refuses new attributes -> weak side cache
+        __slots__ = ("__weakref__",)
+
+    gs = object.__new__(G.GraphStructure)
+    for obj in (StoreBacked(), Frozen()):
+        assert G._cache_get(obj) is None
+        G._cache_put(obj, gs)
+        assert G._cache_get(obj) is gs
+    sb = StoreBacked()
+    G._cache_put(sb, gs)
+    assert G._CACHE_ATTR not in sb.__dict__ and G._cache_get(sb) is gs

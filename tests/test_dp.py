@@ -68,3 +68,59 @@ def test_bucketed_allreduce_world2(tmp_path):
         assert torch.allclose(g0, torch.full((5, 3), 1.5))
         assert torch.allclose(g1, torch.arange(7.0) * 1.5)
         assert reused
+
+
+def _bucket_worker(rank, world, port, outdir):
+    from graphgps_b200.dp import GradBucket
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+
+    class Toy(torch.nn.Module):   # parameter names of a GPSLayer: early group = FFN / norms / out-proj
+        def __init__(self):
+            super().__init__()
+            self.local_model = torch.nn.Linear(3, 5)
+            self.ff_linear1 = torch.nn.Linear(3, 6)
+            self.norm2 = torch.nn.BatchNorm1d(3)
+
+    layers = [Toy(), Toy()]
+    bucket = GradBucket(layers)
+    ptrs = [p.grad.data_ptr() for l in layers for p in l.parameters()]
+    for l in layers:
+        for p in l.parameters():
+            p.grad.fill_(float(rank + 1))            # writes land in the flat buffer
+    assert float(bucket.flat.sum()) == float(rank + 1) * sum(p.numel() for l in layers for p in l.parameters())
+    early0 = bucket.segment(0, True)
+    late0 = bucket.segment(0, False)
+    bucket.allreduce(segments=[early0])              # partial collective first (overlap pattern) ...
+    part = float(layers[0].ff_linear1.weight.grad[0, 0]), float(layers[0].local_model.weight.grad[0, 0])
+    bucket.allreduce(segments=[late0, bucket.segment(1, True), bucket.segment(1, False)])   # ... then the rest
+    same_ptrs = ptrs == [p.grad.data_ptr() for l in layers for p in l.parameters()]
+    vals = [float(p.grad.flatten()[0]) for l in layers for p in l.parameters()]
+    torch.save((rank, part, vals, same_ptrs, early0.numel(), late0.numel()), os.path.join(outdir, f"b{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_bucket_in_place_allreduce_world2(tmp_path):
+    ctx = mp.get_context("spawn")
+
+    def run():
+        port = _free_port()
+        procs = [ctx.Process(target=_bucket_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=120)
+        ok = all(p.exitcode == 0 for p in procs)
+        for p in procs:
+            if p.is_alive():
+                p.kill()
+        return ok
+
+    assert run() or run()
+    for rank in range(2):
+        r, part, vals, same_ptrs, n_early, n_late = torch.load(os.path.join(str(tmp_path), f"b{rank}.pt"))
+        assert part == (1.5, float(rank + 1))        # early segment reduced, late segment still local
+        assert all(v == 1.5 for v in vals) and same_ptrs
+        assert n_early >= 6 * 3 + 6 + 3 + 3 and n_late >= 5 * 3 + 5

@@ -1,0 +1,159 @@
+"""GPU: the data-parallel step as bench.py runs it - static gradient bucket, CUDA-graph replay, in-place NCCL
+all-reduce - must produce mean-over-ranks gradients equal to the oracle's (graphgps/train/custom_train.py:32-38 is
+where the reference's backward()/step() pair sits).  The 1-process variant pins the graph-replay half (the replayed
+backward writes the memory the collective/optimiser reads); the 2-GPU variant adds NCCL and is skipped on 1 GPU."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import graphgps_b200
+from graphgps_b200.batch import make_batch
+from graphgps_b200.dp import GradBucket
+from graphgps_b200.graph import graph_of
+from oracle.gps_oracle import OracleGPSLayer
+from util import rel_err, rel_l2
+
+pytestmark = pytest.mark.gpu
+D, H, NG = 64, 4, 12
+
+
+def _oracle_grads(state, b, ct_x, ct_e):
+    ora = OracleGPSLayer(D, "CustomGatedGCN", "Transformer", H).double()
+    ora.load_state_dict(state)
+    bb = b.clone()
+    bb.x, bb.edge_attr = bb.x.double(), bb.edge_attr.double()
+    out = ora(bb)
+    ((out.x * ct_x.double()).sum() + (out.edge_attr * ct_e.double()).sum()).backward()
+    return {n: p.grad.float() for n, p in ora.named_parameters()}
+
+
+def _make(dev, seed0, nbatch):
+    torch.manual_seed(0)
+    ora = OracleGPSLayer(D, "CustomGatedGCN", "Transformer", H)
+    state = {k: v.clone() for k, v in ora.state_dict().items()}
+    layer = graphgps_b200.GPSLayer(D, "CustomGatedGCN", "Transformer", H)
+    layer.load_state_dict(state)
+    layer = layer.to(dev).train()
+    batches = [make_batch("zinc-gatedgcn", seed=seed0 + i, dim=D, num_graphs=NG) for i in range(nbatch)]
+    g = torch.Generator().manual_seed(5)
+    cts = [(torch.randn(b.x.shape, generator=g), torch.randn(b.edge_attr.shape, generator=g)) for b in batches]
+    return state, layer, batches, cts
+
+
+def _capture_steps(layer, bucket, batches, cts, dev, collective=None):
+    """One CUDA graph per batch: zero bucket -> forward -> backward (-> collective).  Returns the graphs."""
+    dbs = [b.clone().to(dev) for b in batches]
+    dcts = [(cx.to(dev), ce.to(dev)) for cx, ce in cts]
+    for b in dbs:
+        graph_of(b)
+
+    def body(i):
+        b = dbs[i]
+        bb = graphgps_b200.GraphBatch(x=b.x, edge_index=b.edge_index, edge_attr=b.edge_attr, batch=b.batch,
+                                      num_graphs=b.num_graphs)
+        bb.__dict__["_gps_b200_graph"] = b.__dict__["_gps_b200_graph"]
+        bucket.zero_()
+        out = layer(bb)
+        torch.autograd.backward([out.x, out.edge_attr], list(dcts[i]))
+        if collective is not None:
+            collective()
+
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for i in range(len(dbs)):
+            body(i)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    graphs = []
+    for i in range(len(dbs)):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body(i)
+        graphs.append(g)
+    return graphs
+
+
+def _check(named, ref, what):
+    for n, g in ref.items():
+        got = named[n].grad.detach().cpu()
+        assert rel_err(got, g) < 1e-3 or rel_l2(got, g) < 5e-3, (what, n, rel_err(got, g), rel_l2(got, g))
+
+
+def test_bucket_views_survive_graph_replay_single_process():
+    dev = torch.device("cuda:0")
+    state, layer, batches, cts = _make(dev, seed0=11, nbatch=3)
+    bucket = GradBucket([layer])
+    named = dict(layer.named_parameters())
+    ptrs = {n: p.grad.data_ptr() for n, p in named.items()}
+    graphs = _capture_steps(layer, bucket, batches, cts, dev)
+    for i in (2, 0, 1, 0):   # any replay order: .grad must hold THAT batch's gradients afterwards
+        graphs[i].replay()
+        torch.cuda.synchronize()
+        assert all(named[n].grad.data_ptr() == ptrs[n] for n in named)
+        lo = bucket.flat.data_ptr()
+        assert all(lo <= p.grad.data_ptr() < lo + bucket.flat.numel() * 4 for p in named.values())
+        _check(named, _oracle_grads(state, batches[i], *cts[i]), f"replay batch {i}")
+    # accumulation semantics: two backward passes without zeroing in between add up
+    bucket.zero_()
+    for _ in range(2):
+        b = batches[0].clone().to(dev)
+        out = layer(b)
+        torch.autograd.backward([out.x, out.edge_attr], [cts[0][0].to(dev), cts[0][1].to(dev)])
+    torch.cuda.synchronize()
+    ref = _oracle_grads(state, batches[0], *cts[0])
+    _check(named, {n: 2 * g for n, g in ref.items()}, "accumulate x2")
+
+
+def _nccl_worker(rank, world, port, outdir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    state, layer, batches, cts = _make(dev, seed0=100 * (rank + 1), nbatch=2)
+    bucket = GradBucket([layer])
+    dist.all_reduce(torch.zeros(1, device=dev))   # communicator up before capture
+    graphs = _capture_steps(layer, bucket, batches, cts, dev, collective=lambda: bucket.allreduce())
+    res = {}
+    for i in (1, 0):
+        graphs[i].replay()
+        torch.cuda.synchronize()
+        res[i] = {n: p.grad.detach().cpu().clone() for n, p in layer.named_parameters()}
+    torch.save(res, os.path.join(outdir, f"rank{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_replay_then_allreduce_equals_mean_of_oracle_grads_2gpu(tmp_path):
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+    assert all(p.exitcode == 0 for p in procs)
+    got = [torch.load(os.path.join(str(tmp_path), f"rank{r}.pt")) for r in range(2)]
+    for i in (0, 1):
+        # oracle gradients of each rank's batch i, then their mean
+        per_rank = []
+        for r in range(2):
+            torch.manual_seed(0)
+            ora = OracleGPSLayer(D, "CustomGatedGCN", "Transformer", H)
+            state = ora.state_dict()
+            batches = [make_batch("zinc-gatedgcn", seed=100 * (r + 1) + k, dim=D, num_graphs=NG) for k in range(2)]
+            g = torch.Generator().manual_seed(5)
+            cts = [(torch.randn(b.x.shape, generator=g), torch.randn(b.edge_attr.shape, generator=g)) for b in batches]
+            per_rank.append(_oracle_grads(state, batches[i], *cts[i]))
+        for n in per_rank[0]:
+            mean = 0.5 * (per_rank[0][n] + per_rank[1][n])
+            for r in range(2):
+                e, l2 = rel_err(got[r][i][n], mean), rel_l2(got[r][i][n], mean)
+                assert e < 1e-3 or l2 < 5e-3, (i, n, r, e, l2)
+            assert torch.equal(got[0][i][n], got[1][i][n])   # every rank holds the same reduced gradient

@@ -13,16 +13,16 @@ from graphgps_b200 import _lib
 from graphgps_b200.batch import batch_from_lists, make_batch
 from graphgps_b200.graph import GraphStructure, graph_of
 from oracle.gps_oracle import OracleGPSLayer
-from util import compare, golden_batch, golden_names, load_golden, rel_err, run_layer
+from util import compare, golden_batch, golden_names, load_golden, rel_err, rel_l2, run_layer
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 TOL = {"fp32": 1e-3, "bf16": 1e-2}
 # Gradient fallback criterion (util.compare): relative L2 when ReLU-kink flips defeat the max-abs one.
-# bf16 rounding (2^-9) flips ~0.3% of the ReLU masks, and the small golden batches (~140 rows) give
-# BatchNorm little averaging, hence the loose bf16 bound; smooth-activation (GELU) cases are held to
-# the strict max-abs tolerance in test_layer_gelu_strict_gradients_full_size.
-GRAD_L2 = {"fp32": 5e-3, "bf16": 1.5e-1}
+# bf16 rounding (2^-9) flips ~0.3% of the ReLU masks; the L2 bound is 3x the forward tolerance (round 1 allowed
+# 15%, which could hide a defect); smooth-activation (GELU) cases are held to the strict max-abs tolerance in
+# test_layer_gelu_strict_gradients_full_size.  util.compare reports raw max-abs errors beside the scaled ones.
+GRAD_L2 = {"fp32": 5e-3, "bf16": 3e-2}
 
 
 def _stream():
@@ -178,6 +178,18 @@ def test_layer_matches_golden(name, precision):
                                                     ("pcqm4m-small", "GCN", "Transformer", 4),
                                                     ("zinc-gine", "GCN", "Performer", 4)])
 def test_layer_matches_oracle_full_size(shape, local, glob, heads):
+    _full_size(shape, local, glob, heads, "fp32")
+
+
+@pytest.mark.parametrize("shape,local,glob,heads", [("pcqm4m-medium-performer", "CustomGatedGCN", "Performer", 16),
+                                                    ("pcqm4m-small", "CustomGatedGCN", "Transformer", 4),
+                                                    ("code2", "CustomGatedGCN", "Transformer", 4)])
+def test_layer_matches_oracle_full_size_bf16(shape, local, glob, heads):
+    """BASELINE's stated C4 mode (Performer d=384 H=16, bf16) and the C3 / C5 shapes in bf16: 1e-2 forward."""
+    _full_size(shape, local, glob, heads, "bf16")
+
+
+def _full_size(shape, local, glob, heads, precision):
     """BASELINE-size batch: CUDA layer vs the oracle on the same seeded inputs and weights.
 
     Forward outputs: 1e-3 max-abs against the fp64 and the fp32 oracle.  Gradients: 1e-3 max-abs or,
@@ -188,7 +200,7 @@ def test_layer_matches_oracle_full_size(shape, local, glob, heads):
     spec = graphgps_b200.SHAPES[shape]
     torch.manual_seed(0)
     ora = OracleGPSLayer(spec.dim, local, glob, heads)
-    ours = graphgps_b200.GPSLayer(spec.dim, local, glob, heads)
+    ours = graphgps_b200.GPSLayer(spec.dim, local, glob, heads, precision=precision)
     ours.load_state_dict(ora.state_dict())
     ours = ours.to(DEV)
     b = make_batch(shape, seed=7)
@@ -196,8 +208,14 @@ def test_layer_matches_oracle_full_size(shape, local, glob, heads):
     fix = {"config": dict(local=local), "ct_x": torch.randn(b.x.shape, generator=g),
            "ct_e": torch.randn(b.edge_attr.shape, generator=g)}
     ref64 = run_layer(copy.deepcopy(ora).double(), _to(b.clone(), "cpu", torch.float64), fix)
-    ref32 = run_layer(ora, b.clone(), fix)
     res = run_layer(ours, b.clone().to(DEV), fix)
+    if precision == "bf16":
+        t = {k: ref64[k] for k in ("out_x", "out_e", "grad_x", "grad_e") if k in ref64}
+        t["grad_params"], t["state_after"] = ref64["grad_params"], ref64["state_after"]
+        errs = compare(res, t, TOL["bf16"], f"CUDA bf16 vs oracle fp64 @ {shape}", grad_l2_tol=GRAD_L2["bf16"])
+        print(shape, "bf16", {k: f"{v:.2e}" for k, v in errs.items() if k.startswith(("out", "raw:out"))})
+        return
+    ref32 = run_layer(ora, b.clone(), fix)
 
     def target(ref):
         t = {k: ref[k] for k in ("out_x", "out_e", "grad_x", "grad_e") if k in ref}
@@ -449,3 +467,149 @@ def test_cuda_graph_replay_matches_eager_and_redraws_dropout():
     y1, gx1 = y.clone(), gx_static.clone()
     y_eager = body().detach()
     assert rel_err(y1.cpu(), y_eager.cpu()) < 1e-6 and rel_err(gx1.cpu(), x.grad.cpu()) < 1e-6
+
+
+# ------------------------------------------------------------------------------- round-2 additions
+def test_performer_attn_dropout_matches_oracle_with_injected_masks():
+    """SelfAttention ends with dropout(p=attn_dropout) on to_out(out) (performer_layer.py:501-503; built with
+    dropout=self.attn_dropout at gps_layer.py:112-114) before GPSLayer.dropout_attn.  The library's Philox masks for
+    that site (GPS_SITE_PERF_OUT = 7) and for dropout_attn (site 4) are replayed through gps_dropout_mask and
+    injected into the oracle, so the comparison is exact - forward, gradients and running statistics."""
+    import copy
+    from oracle.gps_oracle import to_dense_batch
+    lib = _lib.load()
+    d, heads, pa, pd = 64, 4, 0.5, 0.2
+    torch.manual_seed(3)
+    ora = OracleGPSLayer(d, "CustomGatedGCN", "Performer", heads, dropout=0.0, attn_dropout=0.0)
+    ours = graphgps_b200.GPSLayer(d, "CustomGatedGCN", "Performer", heads, dropout=pd, attn_dropout=pa)
+    ours.load_state_dict(ora.state_dict())
+    ours = ours.to(DEV).train()
+    b = make_batch("zinc-gatedgcn", seed=8, dim=d, num_graphs=9)
+    N = b.num_nodes
+    base = 21 * 4096
+    _set_dropout_counter(base)
+    seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+    masks = {}
+    for site, p in ((7, pa), (4, pd), (1, pd), (2, pd), (5, pd), (6, pd)):
+        rows, cols = (b.num_edges, d) if site == 2 else ((N, 2 * d) if site == 5 else (N, d))
+        m = torch.empty(rows, cols, device=DEV)
+        _lib.check(lib.gps_dropout_mask(m.data_ptr(), rows, cols, p, seed, base + 4096, site, _stream()), "mask")
+        masks[site] = (m.cpu().double() / (1.0 - p))
+
+    class Fixed(torch.nn.Module):
+        def __init__(self, m, dense=None):
+            super().__init__()
+            self.m, self.dense = m, dense
+
+        def forward(self, t):
+            if self.dense is not None:          # the Performer's dropout sees the padded dense batch
+                md, _ = to_dense_batch(self.m, self.dense, None)
+                return t * md
+            return t * self.m
+
+    o64 = copy.deepcopy(ora).double()
+    o64.self_attn.dropout = Fixed(masks[7], dense=b.batch)
+    o64.dropout_attn = Fixed(masks[4])
+    _inject_gatedgcn_dropout(o64.local_model, masks[1], masks[2])
+    o64.ff_dropout1, o64.ff_dropout2 = Fixed(masks[5]), Fixed(masks[6])
+    g = torch.Generator().manual_seed(4)
+    fix = {"config": dict(local="CustomGatedGCN"), "ct_x": torch.randn(b.x.shape, generator=g),
+           "ct_e": torch.randn(b.edge_attr.shape, generator=g)}
+    ref = run_layer(o64, _to(b.clone(), "cpu", torch.float64), fix)
+    res = run_layer(ours, b.clone().to(DEV), fix)
+    tgt = {k: ref[k] for k in ("out_x", "out_e", "grad_x", "grad_e")}
+    tgt["grad_params"], tgt["state_after"] = ref["grad_params"], ref["state_after"]
+    compare(res, tgt, 1e-3, "Performer with attn_dropout / dropout masks injected", grad_l2_tol=5e-3)
+    # and the masks matter: without the attn_dropout site the outputs differ visibly
+    o_plain = copy.deepcopy(ora).double()
+    with torch.no_grad():
+        plain = o_plain(_to(b.clone(), "cpu", torch.float64)).x
+    assert rel_err(res["out_x"], plain.float()) > 1e-2
+
+
+def _inject_gatedgcn_dropout(local, mx, me):
+    """The oracle's GatedGCN applies F.dropout(x, p, training) inline (gatedgcn_layer.py:79-80): patch its p to 0 and
+    multiply through a forward hook instead is not possible without touching the oracle, so wrap its forward."""
+    import torch.nn.functional as F
+    orig = local.forward
+
+    def fwd(x, e, edge_index):
+        calls = []
+        real = F.dropout
+
+        def fake(t, p=0.5, training=True, inplace=False):
+            calls.append(1)
+            return t * (mx if len(calls) == 1 else me)
+        F.dropout = fake
+        try:
+            return orig(x, e, edge_index)
+        finally:
+            F.dropout = real
+    local.forward = fwd
+
+
+def test_three_layer_stack_matches_reference_stack():
+    """GPSModel chains L GPSLayers, each consuming the previous layer's batch.x AND batch.edge_attr
+    (graphgps/network/gps_model.py:100,105-108).  Three CUDA layers chained vs three reference-verbatim layers
+    (oracle/_ref under the shim; the oracle restatement when the reference files are absent), fp64 target:
+    outputs, input gradients and every layer's parameter gradients."""
+    from oracle.ref_shim import find_reference_layer_dir, load_reference
+    d, heads, L = 64, 4, 3
+    torch.manual_seed(11)
+    if find_reference_layer_dir() is not None:
+        mk = lambda: load_reference().GPSLayer(d, "CustomGatedGCN", "Transformer", heads)   # noqa: E731
+    else:
+        mk = lambda: OracleGPSLayer(d, "CustomGatedGCN", "Transformer", heads)              # noqa: E731
+    refs = [mk() for _ in range(L)]
+    ours = []
+    for r in refs:
+        m = graphgps_b200.GPSLayer(d, "CustomGatedGCN", "Transformer", heads)
+        m.load_state_dict(r.state_dict(), strict=True)
+        ours.append(m.to(DEV).train())
+    b = make_batch("zinc-gatedgcn", seed=13, dim=d, num_graphs=24)
+    g = torch.Generator().manual_seed(6)
+    ct_x, ct_e = torch.randn(b.x.shape, generator=g), torch.randn(b.edge_attr.shape, generator=g)
+
+    def run(layers, bb, dev, dt):
+        bb.x.requires_grad_(True)
+        bb.edge_attr.requires_grad_(True)
+        x_in, e_in = bb.x, bb.edge_attr
+        for layer in layers:
+            bb = layer(bb)
+        ((bb.x * ct_x.to(dev, dt)).sum() + (bb.edge_attr * ct_e.to(dev, dt)).sum()).backward()
+        return (bb.x.detach().cpu(), bb.edge_attr.detach().cpu(), x_in.grad.cpu(), e_in.grad.cpu(),
+                [{n: p.grad.detach().cpu() for n, p in layer.named_parameters() if p.grad is not None} for layer in layers])
+
+    rb = _to(b.clone(), "cpu", torch.float64)
+    r = run([m.double() for m in refs], rb, "cpu", torch.float64)
+    o = run(ours, b.clone().to(DEV), DEV, torch.float32)
+    for name, a, t in (("x", o[0], r[0]), ("e", o[1], r[1])):
+        assert rel_err(a, t) < 1e-3, (name, rel_err(a, t))
+    for name, a, t in (("gx", o[2], r[2]), ("ge", o[3], r[3])):
+        assert rel_err(a, t) < 1e-3 or rel_l2(a, t) < 5e-3, (name, rel_err(a, t), rel_l2(a, t))
+    for li in range(L):
+        for n, t in r[4][li].items():
+            a = o[4][li][n]
+            assert rel_err(a, t) < 1e-3 or rel_l2(a, t) < 5e-3, (li, n, rel_err(a, t), rel_l2(a, t))
+
+
+def test_eval_then_train_same_batch_and_retain_graph():
+    """ADVICE r1: the plan cache must not hand an eval-sized saved buffer to a training call on the same (N, E);
+    VERDICT r1: backward(retain_graph=True) followed by a second backward works as on the reference module."""
+    torch.manual_seed(2)
+    layer = graphgps_b200.GPSLayer(64, "CustomGatedGCN", "Transformer", 4).to(DEV)
+    b = make_batch("zinc-gatedgcn", seed=2, dim=64, num_graphs=6).to(DEV)
+    layer.eval()
+    with torch.no_grad():
+        layer(b.clone())
+    layer.train()
+    bb = b.clone()
+    bb.x.requires_grad_(True)
+    x_in = bb.x
+    out = layer(bb)
+    loss = out.x.square().sum()
+    loss.backward(retain_graph=True)
+    g1 = x_in.grad.clone()
+    x_in.grad = None
+    loss.backward()
+    assert rel_err(x_in.grad.cpu(), g1.cpu()) < 1e-6

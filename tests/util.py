@@ -74,12 +74,14 @@ def compare(res, fix, tol, what="", grad_l2_tol=None):
     def check_fwd(key, a, b):
         e = rel_err(a, b)
         errs[key] = e
+        errs["raw:" + key] = float((a.double() - b.double()).abs().max())   # unscaled max-abs beside the scaled one
         if not e <= tol:
             bad[key] = e
 
     def check_grad(key, a, b):
         e = rel_err(a, b)
         errs[key] = e
+        errs["raw:" + key] = float((a.double() - b.double()).abs().max())
         if e <= tol:
             return
         if grad_l2_tol is not None:
