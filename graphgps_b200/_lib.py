@@ -91,6 +91,10 @@ SYMBOLS = {
     "gps_attention_backward": (C.c_int, [C.POINTER(GpsGraph), _i64, _i64, _fp, _fp, _fp, _i64, _fp, _fp, _i64,
                                          _fp, _fp, _fp, _fp, _fp, _i64, _f32, _u64, _u64, _fp]),
     "gps_dropout_mask": (C.c_int, [_fp, _i64, _i64, _f32, _u64, _u64, _i32, _fp]),
+    "gps_to_planes": (C.c_int, [_fp, _i64, _i64, _i64, _fp, _fp, _i64, _fp]),
+    "gps_gemm_planes": (C.c_int, [_fp, _fp, _i64, _i32, _fp, _fp, _i64, _i32, _fp, _i64, _fp, _fp, _i64, _i64, _i64, _i64,
+                                  _i32, _i32, _fp, _fp]),
+    "gps_fallback_count": (C.c_ulonglong, []),
     # not in the header's stage list but part of the ABI: launch counter for bench.py
     "gps_launch_count": (C.c_ulonglong, []),
     "gps_debug_set": (None, [C.c_int]),
@@ -113,7 +117,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
-    if lib.gps_abi_version() != 2:
+    if lib.gps_abi_version() != 3:
         raise RuntimeError("libgps_b200.so ABI version mismatch")
     _lib = lib
     return lib

@@ -80,6 +80,16 @@ __device__ __forceinline__ void store_slice(const float4* src, float* row, int s
     if (ch < nch) st4(row + ch * 4, src[c]);
   }
 }
+// the same slice into the bf16 hi/lo planes of the tensor (operand image of the next GEMM), columns col0 ...
+template <int CH, int LPR>
+__device__ __forceinline__ void store_slice_planes(const float4* src, const Planes& p, int64_t r, int64_t col0, int sub, int nch) {
+  if (!p.hi) return;
+#pragma unroll
+  for (int c = 0; c < CH; ++c) {
+    int ch = sub + c * LPR;
+    if (ch < nch) planes_store4(p, r, col0 + ch * 4, src[c]);
+  }
+}
 template <int CH>
 __device__ __forceinline__ float dot_slice(const float4* a, const float4* b) {
   float s = 0.f;
@@ -97,6 +107,7 @@ struct AttnArgs {
   float scale; float p_drop; uint64_t seed, offset;
   const unsigned long long* offset_dev;
   int role;   // backward: -1 both passes in one grid (blockIdx.z), 0 key-major pass, 1 query-major pass
+  Planes Op, dQp, dKp, dVp;   // optional bf16 hi/lo plane copies of O (forward) / dQ, dK, dV (backward)
 };
 __device__ __forceinline__ uint64_t eff_offset(const AttnArgs& a) {
   return a.offset + ((a.p_drop > 0.f && a.offset_dev) ? *a.offset_dev : 0ull);
@@ -167,6 +178,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_attn_fwd(AttnArgs a) {
 #pragma unroll
     for (int c = 0; c < CH; ++c) o[c] = f4scale(o[c], inv);
     store_slice<CH, LPR>(o, a.O + (int64_t)i * a.ldo + hoff, sub, nch);
+    store_slice_planes<CH, LPR>(o, a.Op, i, hoff, sub, nch);
     if (sub == 0) a.lse[(int64_t)i * a.H + h] = m + __logf(l);
   }
 }
@@ -259,6 +271,7 @@ __device__ __forceinline__ void attn_bwd_q_body(const AttnArgs& a) {
 #pragma unroll
     for (int c = 0; c < CH; ++c) gq[c] = f4scale(gq[c], a.scale);
     store_slice<CH, LPR>(gq, a.dQ + (int64_t)i * a.ldg + hoff, sub, nch);
+    store_slice_planes<CH, LPR>(gq, a.dQp, i, hoff, sub, nch);
   }
 }
 
@@ -331,6 +344,8 @@ __device__ __forceinline__ void attn_bwd_kv_body(const AttnArgs& a) {
   if (row_ok) {
     store_slice<CH, LPR>(gk, a.dK + (int64_t)j * a.ldg + hoff, sub, nch);
     store_slice<CH, LPR>(gv, a.dV + (int64_t)j * a.ldg + hoff, sub, nch);
+    store_slice_planes<CH, LPR>(gk, a.dKp, j, hoff, sub, nch);
+    store_slice_planes<CH, LPR>(gv, a.dVp, j, hoff, sub, nch);
   }
 }
 
@@ -382,9 +397,10 @@ static int dispatch(int which, const AttnArgs& a, cudaStream_t stream) {
 
 int attention_fwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, const float* K, const float* V,
                   int64_t ld, float* O, int64_t ldo, float* lse, float p_drop, uint64_t seed, uint64_t offset,
-                  cudaStream_t stream, const unsigned long long* offset_dev) {
+                  cudaStream_t stream, const unsigned long long* offset_dev, Planes Op) {
   AttnArgs a{};
   a.offset_dev = offset_dev;
+  a.Op = Op;
   a.gptr = g.graph_ptr; a.B = (int)g.B; a.N = (int)g.N; a.H = (int)heads; a.hd = (int)hd;
   a.Q = Q; a.K = K; a.V = V; a.ld = ld; a.O = O; a.ldo = ldo; a.lse = lse;
   a.scale = 1.f / sqrtf((float)hd); a.p_drop = p_drop; a.seed = seed; a.offset = offset;
@@ -395,9 +411,10 @@ int attention_fwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, 
 int attention_bwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, const float* K, const float* V,
                   int64_t ld, const float* O, const float* dO, int64_t ldo, const float* lse, float* delta,
                   float* dQ, float* dK, float* dV, int64_t ldg, float p_drop, uint64_t seed, uint64_t offset,
-                  cudaStream_t stream, const unsigned long long* offset_dev) {
+                  cudaStream_t stream, const unsigned long long* offset_dev, Planes dQp, Planes dKp, Planes dVp) {
   AttnArgs a{};
   a.offset_dev = offset_dev;
+  a.dQp = dQp; a.dKp = dKp; a.dVp = dVp;
   a.gptr = g.graph_ptr; a.B = (int)g.B; a.N = (int)g.N; a.H = (int)heads; a.hd = (int)hd;
   a.Q = Q; a.K = K; a.V = V; a.ld = ld; a.Oc = O; a.dO = dO; a.ldo = ldo; a.lsec = lse;
   a.delta = delta; a.deltac = delta; a.dQ = dQ; a.dK = dK; a.dV = dV; a.ldg = ldg;

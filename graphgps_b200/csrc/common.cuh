@@ -1,6 +1,7 @@
 // common.cuh — shared device/host helpers for libgps_b200 (sm_100a only).
 #pragma once
 
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -69,8 +70,31 @@ struct Arena {
   }
 };
 
+// bf16 "planes" of an fp32 tensor: plain row-major bf16 matrices holding hi = bf16(v) and lo = bf16(v - hi)
+// (lo == nullptr in precision="bf16" mode).  Written once by the producing kernel, read by the TMA-fed GEMM
+// (gemm_tma.cu) in any operand orientation.  ld is in elements (multiple of 8: 16-byte row pitch for TMA).
+struct Planes {
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  int64_t ld = 0;
+  Planes cols(int64_t c0) const { Planes q = *this; if (q.hi) q.hi += c0; if (q.lo) q.lo += c0; return q; }
+  Planes rows(int64_t r0) const { Planes q = *this; if (q.hi) q.hi += r0 * ld; if (q.lo) q.lo += r0 * ld; return q; }
+};
+
 // ------------------------------------------------------------------------------------ device
 #ifdef __CUDACC__
+
+// hi/lo split of 4 consecutive values of row r starting at column c (c % 4 == 0): one 8-byte store per plane
+__device__ __forceinline__ void planes_store4(const Planes& p, int64_t r, int64_t c, float4 v) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(v.x, v.y), h1 = __floats2bfloat162_rn(v.z, v.w);
+  uint2 hw = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+  *reinterpret_cast<uint2*>(p.hi + r * p.ld + c) = hw;
+  if (p.lo) {
+    __nv_bfloat162 l0 = __floats2bfloat162_rn(v.x - __low2float(h0), v.y - __high2float(h0));
+    __nv_bfloat162 l1 = __floats2bfloat162_rn(v.z - __low2float(h1), v.w - __high2float(h1));
+    *reinterpret_cast<uint2*>(p.lo + r * p.ld + c) = make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+  }
+}
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }

@@ -144,7 +144,7 @@ struct OpBnActRes {
   static constexpr int NS = STATS ? 2 : 0;
   const float* z; int64_t ldz;
   const float* R; float* out; int64_t d;
-  BnView bn; int act; DropCfg drop; double* stats;
+  BnView bn; int act; DropCfg drop; double* stats; Planes outp;
   BnRegs reg;
   __device__ void prepare(int c4) {
     reg.load(bn, c4);
@@ -156,6 +156,7 @@ struct OpBnActRes {
       v = f4mul(v, dropout_scale4(drop.p, drop.seed, drop.offset, drop.site, (uint64_t)r * (d >> 2) + c4));
     if (R) v = f4add(v, ld4(R + r * d + c4 * 4));
     st4(out + r * d + c4 * 4, v);
+    if (outp.hi) planes_store4(outp, r, c4 * 4, v);
     if (STATS) {
       acc[0] = f4add(acc[0], v);
       acc[1] = f4fma(v, v, acc[1]);
@@ -169,7 +170,7 @@ struct OpBnActRes {
 struct OpCombine {
   static constexpr int NS = 0;
   const float* a; const float* b; float* out; int64_t d;
-  BnView bna, bnb;
+  BnView bna, bnb; Planes outp;
   BnRegs ra, rb;
   __device__ void prepare(int c4) {
     ra.load(bna, c4);
@@ -179,6 +180,7 @@ struct OpCombine {
     float4 v = ra.apply(ld4(a + r * d + c4 * 4));
     if (b) v = f4add(v, rb.apply(ld4(b + r * d + c4 * 4)));
     st4(out + r * d + c4 * 4, v);
+    if (outp.hi) planes_store4(outp, r, c4 * 4, v);
   }
   __device__ double* stat_ptr(int) { return nullptr; }
   __device__ void finish(int, int) {}
@@ -217,7 +219,7 @@ struct OpBnBwdApply {
   static constexpr int NS = 0;
   const float* g; int64_t ldg; const float* z; int64_t ldz; int64_t d;
   BnView bn; int act; DropCfg drop; const double* sums; float inv_n;
-  float* out; int64_t ldo; float* grad_gamma; float* grad_beta; int accumulate;
+  float* out; int64_t ldo; float* grad_gamma; float* grad_beta; int accumulate; Planes outp;
   BnRegs reg;
   float4 m1, m2, gs;  // S1/n, S2/n, gamma*invstd
   float4 s1raw, s2raw;
@@ -238,6 +240,7 @@ struct OpBnBwdApply {
     float4 v = make_float4(gs.x * (gp.x - m1.x - zh.x * m2.x), gs.y * (gp.y - m1.y - zh.y * m2.y),
                            gs.z * (gp.z - m1.z - zh.z * m2.z), gs.w * (gp.w - m1.w - zh.w * m2.w));
     st4(out + r * ldo + c4 * 4, v);
+    if (outp.hi) planes_store4(outp, r, c4 * 4, v);
   }
   __device__ double* stat_ptr(int) { return nullptr; }
   __device__ void finish(int c4, int ry) {
@@ -298,18 +301,18 @@ static int launch_rowwise(Op op, int64_t rows, int64_t d, cudaStream_t stream) {
 }  // namespace
 
 int bn_act_residual(const float* z, int64_t ldz, const float* R, float* out, int64_t rows, int64_t d, BnView bn,
-                    int act, DropCfg drop, double* stats, cudaStream_t stream) {
+                    int act, DropCfg drop, double* stats, cudaStream_t stream, Planes outp) {
   if (stats) {
-    OpBnActRes<true> op{z, ldz, R, out, d, bn, act, drop, stats};
+    OpBnActRes<true> op{z, ldz, R, out, d, bn, act, drop, stats, outp};
     return launch_rowwise(op, rows, d, stream);
   }
-  OpBnActRes<false> op{z, ldz, R, out, d, bn, act, drop, nullptr};
+  OpBnActRes<false> op{z, ldz, R, out, d, bn, act, drop, nullptr, outp};
   return launch_rowwise(op, rows, d, stream);
 }
 
 int bn_combine(const float* a, BnView bna, const float* b, BnView bnb, float* out, int64_t rows, int64_t d,
-               cudaStream_t stream) {
-  OpCombine op{a, b, out, d, bna, bnb};
+               cudaStream_t stream, Planes outp) {
+  OpCombine op{a, b, out, d, bna, bnb, outp};
   return launch_rowwise(op, rows, d, stream);
 }
 
@@ -321,9 +324,9 @@ int bn_bwd_reduce(const float* g, int64_t ldg, const float* z, int64_t ldz, int6
 
 int bn_bwd_apply(const float* g, int64_t ldg, const float* z, int64_t ldz, int64_t rows, int64_t d, BnView bn,
                  int act, DropCfg drop, const double* sums, float* out, int64_t ldo, float* grad_gamma,
-                 float* grad_beta, cudaStream_t stream, bool accumulate) {
+                 float* grad_beta, cudaStream_t stream, bool accumulate, Planes outp) {
   OpBnBwdApply op{g, ldg, z, ldz, d, bn, act, drop, sums, 1.f / (float)(rows > 0 ? rows : 1),
-                  out, ldo, grad_gamma, grad_beta, accumulate ? 1 : 0};
+                  out, ldo, grad_gamma, grad_beta, accumulate ? 1 : 0, outp};
   if (rows == 0) {
     // no rows: gradients of gamma/beta are zero
     if (grad_gamma && !accumulate) GPS_CUDA(cudaMemsetAsync(grad_gamma, 0, d * sizeof(float), stream));

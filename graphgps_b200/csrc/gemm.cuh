@@ -36,7 +36,18 @@ struct GemmParams {
   // bpk_mn: the image is MN-major (tb == 1: B is [K x N]; bpk_groups = 64-column blocks per k-block)
   const void* bpk = nullptr; int64_t bpk_lo_off = 0; int bpk_groups = 0; int bpk_row0 = 0; int bpk_mn = 0;
   int bpk_kb0 = 0;   // first 64-deep k-block of this GEMM inside the packed planes (reduction sub-range of a packed matrix)
+  // bf16 hi/lo planes of the operands as stored (A: [M,K] or, ta == 1, [K,M]; B: [N,K] or, tb == 1, [K,N]): when both
+  // are given the TMA-fed kernel (gemm_tma.cu) runs and A/B (fp32) are not read.  Cp: optional plane copy of the
+  // result for the next GEMM; C may then be null (planes-only output).
+  Planes Ap, Bp, Cp;
 };
+
+struct ToPlanesItem { const float* src; int64_t ld; int rows; int cols; Planes dst; };
+// fp32 [rows, cols] (pitch ld) -> bf16 hi/lo planes, up to 16 matrices per launch
+int to_planes(const ToPlanesItem* items, int n, cudaStream_t stream);
+// TMA-fed tcgen05 product on plane operands; GPS_ERR_UNSUPPORTED when the planes are missing / misaligned
+int gemm_tma(const GemmParams& p, cudaStream_t stream);
+void gemm_tma_set_force_bn(int bn);
 
 // Pre-packs up to 8 weight matrices (fp32 [rows, K] row-major) into the tcgen05 kernel's shared-memory tile image.
 // K-major (mn = 0): W is [rows x K], dst sized by prepack_bytes(rows, K).

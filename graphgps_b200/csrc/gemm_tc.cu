@@ -27,6 +27,7 @@
 #include <algorithm>
 
 #include "gemm.cuh"
+#include "tc_ptx.cuh"
 
 namespace gps {
 
@@ -40,101 +41,7 @@ constexpr int kMmaWarp = kProducerWarps;
 constexpr int kThreads = (kMmaWarp + 1) * 32;
 constexpr int kATileBytes = BM * BK * 2;       // 16 KB
 constexpr int kBBlockBytes = 64 * BK * 2;      // 8 KB per 64 columns of B
-constexpr uint32_t kSpinLimit = 1u << 28;
-
-// ------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > kSpinLimit) __trap();  // never hang the GPU: a protocol bug becomes an error
-  }
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// 1-D bulk TMA: global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
-  uint32_t r[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// UMMA shared-memory descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= 1ull << 46;   // descriptor version (Blackwell)
-  d |= 2ull << 61;   // layout type SWIZZLE_128B
-  return d;
-}
-
-// fp32 x8 -> bf16 hi (and residual lo) packed as 16 bytes each
-__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
-  uint32_t h[4], l[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    __nv_bfloat162 hb = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-    float r0 = v[2 * i] - __low2float(hb), r1 = v[2 * i + 1] - __high2float(hb);
-    __nv_bfloat162 lb = __floats2bfloat162_rn(r0, r1);
-    h[i] = *reinterpret_cast<uint32_t*>(&hb);
-    l[i] = *reinterpret_cast<uint32_t*>(&lb);
-  }
-  hi = make_uint4(h[0], h[1], h[2], h[3]);
-  lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
+using namespace tc;   // PTX wrappers: tc_ptx.cuh
 
 // Byte offset of chunk `c` inside an operand tile stored in the canonical SWIZZLE_128B layout.
 //  K-major : rows of 128 B (64 bf16 of K), 8-row groups of 1024 B.
@@ -644,7 +551,7 @@ __global__ void k_prepack_weights(PrepackDesc d) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = (row < it.rows && k + i < it.K) ? it.W[(int64_t)row * it.ld + k + i] : 0.f;
     }
-    split8(v, hi, lo);
+    tc::split8(v, hi, lo);
     const int64_t plane = (int64_t)nkb * groups * 1024;
     uint8_t* base = reinterpret_cast<uint8_t*>(it.dst) + ((int64_t)kb * groups + grp) * 1024 + r * 128 + ((ck ^ r) << 4);
     *reinterpret_cast<uint4*>(base) = hi;
@@ -662,7 +569,7 @@ __global__ void k_prepack_weights(PrepackDesc d) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = (k < it.K && col + i < it.rows) ? it.W[(int64_t)k * it.ld + col + i] : 0.f;
     }
-    split8(v, hi, lo);
+    tc::split8(v, hi, lo);
     const int64_t plane = (int64_t)nkb * cblocks * 8192;
     uint8_t* base = reinterpret_cast<uint8_t*>(it.dst) + ((int64_t)kb * cblocks + cb) * 8192 + kg * 1024 + r * 128 +
                     ((ck ^ r) << 4);

@@ -37,10 +37,10 @@ struct DropCfg {
 // ---- forward row-wise stages ----------------------------------------------------------------
 // out = R + dropout(act(BN(z)))  [+ column sums of out into stats]   (gatedgcn_layer.py:72-83)
 int bn_act_residual(const float* z, int64_t ldz, const float* R, float* out, int64_t rows, int64_t d,
-                    BnView bn, int act, DropCfg drop, double* stats, cudaStream_t stream);
+                    BnView bn, int act, DropCfg drop, double* stats, cudaStream_t stream, Planes outp = Planes());
 // out = BN_a(a) [+ BN_b(b)]   (gps_layer.py:194,217,222 and :229)
 int bn_combine(const float* a, BnView bna, const float* b, BnView bnb, float* out, int64_t rows, int64_t d,
-               cudaStream_t stream);
+               cudaStream_t stream, Planes outp = Planes());
 
 // ---- backward row-wise stages ---------------------------------------------------------------
 // g' = g * [act'(BN(z))] * [dropout scale];  sums[0][c] += sum_r g', sums[1][c] += sum_r g' * zhat
@@ -49,7 +49,7 @@ int bn_bwd_reduce(const float* g, int64_t ldg, const float* z, int64_t ldz, int6
 // out = gamma*invstd*(g' - S1/n - zhat*S2/n) (+ add); also writes grad_gamma = S2, grad_beta = S1
 int bn_bwd_apply(const float* g, int64_t ldg, const float* z, int64_t ldz, int64_t rows, int64_t d, BnView bn,
                  int act, DropCfg drop, const double* sums, float* out, int64_t ldo, float* grad_gamma,
-                 float* grad_beta, cudaStream_t stream, bool accumulate = false);
+                 float* grad_beta, cudaStream_t stream, bool accumulate = false, Planes outp = Planes());
 // out = a + b (+ c)   row-wise with independent leading dimensions
 int add3(const float* a, int64_t lda, const float* b, int64_t ldb, const float* c, int64_t ldc, float* out,
          int64_t ldo, int64_t rows, int64_t d, cudaStream_t stream);
@@ -66,12 +66,13 @@ int gatedgcn_fwd(const GpsGraph& g, int64_t d, const float* Ax, const float* Bx,
 // and the total gradient w.r.t. e_ij on exit; writes g_num [N,d] and g_Dx (ld ldg).
 int gatedgcn_bwd_dst(const GpsGraph& g, int64_t d, const float* g_xt, int64_t ldg, const float* ehat,
                      const float* Bx, int64_t ldy, float* g_e, float* g_num, float* g_Dx,
-                     cudaStream_t stream);
+                     cudaStream_t stream, Planes g_e_p = Planes(), Planes g_Dx_p = Planes());
 // src-ordered backward pass: g_Ex_j = sum g_e_k, g_Bx_j = sum g_num[dst(k)] * sigmoid(ehat_k)
 int gatedgcn_bwd_src(const GpsGraph& g, int64_t d, const float* g_e, const float* ehat, const float* g_num,
-                     float* g_Ex, float* g_Bx, int64_t ldg, cudaStream_t stream);
+                     float* g_Ex, float* g_Bx, int64_t ldg, cudaStream_t stream, Planes g_Ex_p = Planes(),
+                     Planes g_Bx_p = Planes());
 int gine_fwd(const GpsGraph& g, int64_t d, const float* x, const float* e, float eps, float* out,
-             cudaStream_t stream);
+             cudaStream_t stream, Planes outp = Planes());
 // g_e[k] = g_o[dst(k)] * [x_src + e_k > 0];  (dst ordered)
 int gine_bwd_dst(const GpsGraph& g, int64_t d, const float* x, const float* e, const float* g_o, float* g_e,
                  cudaStream_t stream);
@@ -85,15 +86,16 @@ int gcn_dinv(const GpsGraph& g, float* dinv, cudaStream_t stream);
 int gcn_fwd(const GpsGraph& g, int64_t d, const float* Y, int64_t ldy, const float* dinv, const float* bias,
             const float* x, float* xloc, DropCfg drop, double* stats, cudaStream_t stream);
 int gcn_bwd(const GpsGraph& g, int64_t d, const float* g_h, const float* dinv, float* gY, int64_t ldg,
-            cudaStream_t stream);
+            cudaStream_t stream, Planes gYp = Planes());
 
 // ---- attention ------------------------------------------------------------------------------
 int attention_fwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, const float* K, const float* V,
                   int64_t ld, float* O, int64_t ldo, float* lse, float p_drop, uint64_t seed, uint64_t offset,
-                  cudaStream_t stream, const unsigned long long* offset_dev = nullptr);
+                  cudaStream_t stream, const unsigned long long* offset_dev = nullptr, Planes Op = Planes());
 int attention_bwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, const float* K, const float* V,
                   int64_t ld, const float* O, const float* dO, int64_t ldo, const float* lse, float* delta,
                   float* dQ, float* dK, float* dV, int64_t ldg, float p_drop, uint64_t seed, uint64_t offset,
-                  cudaStream_t stream, const unsigned long long* offset_dev = nullptr);
+                  cudaStream_t stream, const unsigned long long* offset_dev = nullptr, Planes dQp = Planes(),
+                  Planes dKp = Planes(), Planes dVp = Planes());
 
 }  // namespace gps

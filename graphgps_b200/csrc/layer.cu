@@ -57,16 +57,45 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+static std::atomic<unsigned long long> g_fallbacks{0};
+
+// Dispatcher: TMA-fed tcgen05 kernel when the caller supplies operand planes, else the register-staged tcgen05 kernel
+// on the fp32 operands, else (odd shapes / alignment) the exact CUDA-core kernel - counted, and an error under
+// GPS_B200_STRICT=1 so that a 10x slower path can never be taken silently.
 int gemm(const GemmParams& p, cudaStream_t stream) {
-  static const bool force_simt = [] {
+  static const int mode = [] {   // GPS_B200_GEMM: "simt" = CUDA-core only, "tc" = no TMA kernel, default = all
     const char* e = getenv("GPS_B200_GEMM");
-    return e && strcmp(e, "simt") == 0;
+    return e && strcmp(e, "simt") == 0 ? 2 : (e && strcmp(e, "tc") == 0 ? 1 : 0);
   }();
-  if (!force_simt) {
-    int rc = gemm_tc(p, stream);
+  static const bool strict = [] {
+    const char* e = getenv("GPS_B200_STRICT");
+    return e && e[0] == '1';
+  }();
+  if (mode == 0 && p.Ap.hi && p.Bp.hi) {
+    int rc = gemm_tma(p, stream);
     if (rc != GPS_ERR_UNSUPPORTED) return rc;
   }
-  return gemm_simt(p, stream);
+  GPS_REQUIRE(p.A && p.B && p.C, GPS_ERR_UNSUPPORTED, "gemm: plane operands rejected and no fp32 operands to fall back to");
+  GemmParams q = p;
+  if (q.Cp.hi) {   // the fp32 kernels do not write planes: convert afterwards
+    q.Cp = Planes();
+  }
+  int rc = GPS_ERR_UNSUPPORTED;
+  if (mode != 2) rc = gemm_tc(q, stream);
+  if (rc == GPS_ERR_UNSUPPORTED) {
+    if (mode != 2) {
+      g_fallbacks.fetch_add(1, std::memory_order_relaxed);
+      GPS_REQUIRE(!strict, GPS_ERR_UNSUPPORTED,
+                  "GPS_B200_STRICT: dense product M=%d N=%d K=%d (ta=%d tb=%d) would fall back to the CUDA-core kernel",
+                  p.M, p.N, p.K, p.ta, p.tb);
+    }
+    rc = gemm_simt(q, stream);
+  }
+  if (rc == GPS_OK && p.Cp.hi) {
+    ToPlanesItem it{p.C, p.ldc, p.M, p.N, p.Cp};
+    rc = to_planes(&it, 1, stream);
+  }
+  return rc;
 }
 
 namespace {
@@ -177,6 +206,11 @@ struct Plan {
   // the same weights as MN-major planes for the data-gradient GEMMs of the backward pass (training only)
   uint8_t *pt_cat, *pt_C, *pt_out, *pt_ff1, *pt_ff2, *pt_g0, *pt_g1;
   bool prepack;
+  // bf16 hi/lo operand planes of the TMA-fed GEMM (gemm_tma.cu).  Saved: layer inputs, weights and the forward
+  // activations the weight gradients re-read; workspace: the backward gradients that feed GEMMs.
+  bool use_planes;
+  Planes x_p, e_p, O_p, s_p, hid_p, agg_p, h1_p, Wcat_p, C_p, out_p, ff1_p, ff2_p, g0_p, g1_p, pq_p, pk_p, pv_p;
+  Planes gt_p, ghid_p, ghA_p, ge_p, gY1_p, gtmp_p, gtmp2_p, gtmp3_p, gl1_p, gh1_p;
   int64_t saved_bytes;
   // forward workspace
   double* fstats;
@@ -188,6 +222,15 @@ struct Plan {
   int64_t bwd_bytes;
   int64_t fwd_launches, bwd_launches;
 };
+
+// GPS_B200_GEMM=tc|simt keeps the round-1 operand path (register-staged conversion per consuming CTA)
+static bool planes_enabled() {
+  static const bool v = [] {
+    const char* e = getenv("GPS_B200_GEMM");
+    return !(e && (strcmp(e, "tc") == 0 || strcmp(e, "simt") == 0));
+  }();
+  return v;
+}
 
 static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
   memset(P, 0, sizeof(*P));
@@ -275,7 +318,40 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
   if (gelu) P->hid_pre = S.alloc<float>(N * 2 * d);
   P->t = S.alloc<float>(N * d);
   P->prepack = (d % 8 == 0) && (!P->perf || P->inner % 8 == 0);
-  if (P->prepack) {
+  P->use_planes = P->prepack && planes_enabled();
+  const bool lo = a->precision == GPS_PREC_FP32;
+  auto mkplanes = [&](Arena& A, int64_t rows, int64_t cols) {
+    Planes q;
+    q.ld = round_up(cols, 8);
+    q.hi = A.alloc<__nv_bfloat16>(rows * q.ld + 8);
+    q.lo = lo ? A.alloc<__nv_bfloat16>(rows * q.ld + 8) : nullptr;
+    return q;
+  };
+  if (P->use_planes) {
+    const int64_t kout = P->perf ? P->inner : d;
+    P->x_p = mkplanes(S, N, d);
+    if (P->gated || P->gine) P->e_p = mkplanes(S, E, d);
+    if (P->attn || P->perf) P->O_p = mkplanes(S, N, kout);
+    P->s_p = mkplanes(S, N, d);
+    P->hid_p = mkplanes(S, N, 2 * d);
+    if (P->gine) {
+      P->agg_p = mkplanes(S, N, d);
+      P->h1_p = mkplanes(S, N, d);
+      P->g0_p = mkplanes(S, d, d);
+      P->g1_p = mkplanes(S, d, d);
+    }
+    if (P->Wy) P->Wcat_p = mkplanes(S, P->Wy, d);
+    if (P->gated) P->C_p = mkplanes(S, d, d);
+    if (P->attn || P->perf) P->out_p = mkplanes(S, d, kout);
+    P->ff1_p = mkplanes(S, 2 * d, d);
+    P->ff2_p = mkplanes(S, d, 2 * d);
+    if (P->perf) {
+      P->pq_p = mkplanes(S, P->inner, d);
+      P->pk_p = mkplanes(S, P->inner, d);
+      P->pv_p = mkplanes(S, P->inner, d);
+    }
+  }
+  if (P->prepack && !P->use_planes) {
     const int64_t kout = P->perf ? P->inner : d;
     if (P->Wy) P->pk_cat = S.alloc<uint8_t>(prepack_bytes((int)P->Wy, (int)d));
     if (P->gated) P->pk_C = S.alloc<uint8_t>(prepack_bytes((int)d, (int)d));
@@ -349,6 +425,22 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
     P->g_h1 = Bk.alloc<float>(N * d);
     P->g_agg = Bk.alloc<float>(N * d);
     P->g_xl = Bk.alloc<float>(N * d);
+  }
+  if (P->use_planes) {
+    P->gt_p = mkplanes(Bk, N, d);
+    P->ghid_p = mkplanes(Bk, N, 2 * d);
+    if (P->attn || P->perf) P->ghA_p = mkplanes(Bk, N, d);
+    if (P->gated) P->ge_p = mkplanes(Bk, E, d);
+    if (P->Wy) P->gY1_p = mkplanes(Bk, N, P->Wy);
+    if (a->dropout > 0.f || (P->perf && a->attn_dropout > 0.f)) {
+      P->gtmp_p = mkplanes(Bk, N, d);
+      P->gtmp2_p = mkplanes(Bk, N, d);
+      P->gtmp3_p = mkplanes(Bk, N, d);
+    }
+    if (P->gine) {
+      P->gl1_p = mkplanes(Bk, N, d);
+      P->gh1_p = mkplanes(Bk, N, d);
+    }
   }
   P->bwd_bytes = Bk.used;
   return GPS_OK;
@@ -473,7 +565,8 @@ static int splitk_for(int64_t rows, int64_t out = 304, int64_t in = 304) {
 
 // weight gradient of a Linear: dW[out,in] = G[rows,out]^T X[rows,in], db[out] = colsum(G)
 static int linear_wgrad(const float* G, int64_t ldg, const float* X, int64_t ldx, int64_t rows, int64_t out,
-                        int64_t in, float* dW, float* db, int precision, cudaStream_t st) {
+                        int64_t in, float* dW, float* db, int precision, cudaStream_t st, Planes Gp = Planes(),
+                        Planes Xp = Planes()) {
   if (!dW) return GPS_OK;
   if (!g_grads_prezeroed) {
     GPS_CUDA(cudaMemsetAsync(dW, 0, (size_t)(out * in) * sizeof(float), st));
@@ -489,6 +582,13 @@ static int linear_wgrad(const float* G, int64_t ldg, const float* X, int64_t ldx
   if (p.splitk == 1) p.splitk = 2;  // accumulate path (C pre-zeroed) also for tiny inputs
   p.colsum_a = db;
   p.precision = precision;
+  p.Ap = Gp; p.Bp = Xp;
+  if (precision == GPS_PREC_BF16 && Gp.hi && db) {
+    // bf16 mode stores no lo plane: summing ~N bf16-rounded rows would put ~sqrt(N) 2^-9 of noise on a bias gradient
+    // that is often a near-cancelling sum (every Linear here feeds a BatchNorm) -> exact fp32 column sum instead
+    p.colsum_a = nullptr;
+    GPS_TRY(colsum(G, ldg, rows, out, db, st));
+  }
   return gemm(p, st);
 }
 
@@ -538,7 +638,41 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
   // Weight planes: the ones the first GEMMs need are packed on the caller's stream; the rest (output projection,
   // FFN, and the MN-major images the backward pass reads) are packed next to those GEMMs on their own stream.
   cudaStream_t sp = sd ? sd->s4 : st;
-  if (P.prepack) {
+  if (P.use_planes) {
+    // layer inputs and every weight -> bf16 hi/lo planes, one launch (the producers inside the layer write the
+    // planes of their outputs themselves).  Wcat_p rows follow pack_desc(): [A;B;D;E | conv] then in_proj.
+    ToPlanesItem it[16];
+    int ni = 0;
+    auto add = [&](const float* src, int64_t ld, int64_t rows, int64_t cols, Planes dst) {
+      if (src && dst.hi && rows > 0) it[ni++] = ToPlanesItem{src, ld, (int)rows, (int)cols, dst};
+    };
+    const int64_t kout = P.perf ? P.inner : d;
+    add(a->x, d, N, d, P.x_p);
+    if (P.gated || P.gine) add(a->edge_attr, d, E, d, P.e_p);
+    if (P.gated) {
+      add(a->gcn_A.weight, d, d, d, P.Wcat_p.rows(0));
+      add(a->gcn_B.weight, d, d, d, P.Wcat_p.rows(d));
+      add(a->gcn_D.weight, d, d, d, P.Wcat_p.rows(2 * d));
+      add(a->gcn_E.weight, d, d, d, P.Wcat_p.rows(3 * d));
+      add(a->gcn_C.weight, d, d, d, P.C_p);
+    }
+    if (P.gcn) add(a->gcn_conv.weight, d, d, d, P.Wcat_p.rows(0));
+    if (P.attn) add(a->attn_in.weight, d, 3 * d, d, P.Wcat_p.rows(P.qkv_off));
+    if (P.gine) {
+      add(a->gine_lin0.weight, d, d, d, P.g0_p);
+      add(a->gine_lin1.weight, d, d, d, P.g1_p);
+    }
+    if (P.attn || P.perf) add(a->attn_out.weight, kout, d, kout, P.out_p);
+    add(a->ff1.weight, d, 2 * d, d, P.ff1_p);
+    add(a->ff2.weight, 2 * d, d, 2 * d, P.ff2_p);
+    if (P.perf) {
+      add(a->perf_q.weight, d, P.inner, d, P.pq_p);
+      add(a->perf_k.weight, d, P.inner, d, P.pk_p);
+      add(a->perf_v.weight, d, P.inner, d, P.pv_p);
+    }
+    GPS_TRY(to_planes(it, ni, st));
+  }
+  if (P.prepack && !P.use_planes) {
     PrepackItem items[16];
     int ni = 0;
     const int64_t kout = P.perf ? P.inner : d;
@@ -575,6 +709,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.A = a->edge_attr; g.lda = (int)d; g.B = a->gcn_C.weight; g.ldb = (int)d; g.C = P.ehat; g.ldc = (int)d;
     g.bias = a->gcn_C.bias; g.precision = a->precision;
     set_bpk(g, P.pk_C, d, d, 0);
+    g.Ap = P.e_p; g.Bp = P.C_p;
     GPS_TRY(gemm(g, s2));
   }
 
@@ -595,6 +730,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
       g.A = a->x; g.lda = (int)d; g.B = P.Wcat + wl * d; g.ldb = (int)d; g.C = P.Y1 + wl; g.ldc = (int)P.Wy;
       g.bias = P.bcat + wl; g.precision = a->precision;
       set_bpk(g, P.pk_cat, P.Wy, d, wl);
+      g.Ap = P.x_p; g.Bp = P.Wcat_p.rows(wl);
       GPS_TRY(gemm(g, sg));
     }
     if (wl > 0) {
@@ -603,6 +739,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
       g.A = a->x; g.lda = (int)d; g.B = P.Wcat; g.ldb = (int)d; g.C = P.Y1; g.ldc = (int)P.Wy;
       g.bias = P.bcat; g.precision = a->precision;
       set_bpk(g, P.pk_cat, P.Wy, d, 0);
+      g.Ap = P.x_p; g.Bp = P.Wcat_p;
       GPS_TRY(gemm(g, st));
     }
   }
@@ -620,12 +757,13 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(bn_act_residual(P.ehat, d, a->edge_attr, a->edge_out, E, d, bn_view_fwd(P, a, BN_E, a->bn_edge_e, E), act,
                             drop(GPS_SITE_GCN_E), nullptr, st));
   } else if (P.gine) {
-    GPS_TRY(gine_fwd(a->graph, d, a->x, a->edge_attr, a->gine_eps, P.agg, st));
+    GPS_TRY(gine_fwd(a->graph, d, a->x, a->edge_attr, a->gine_eps, P.agg, st, P.agg_p));
     GemmParams g;  // h1 = act(agg W0^T + b0)
     g.M = (int)N; g.N = (int)d; g.K = (int)d;
     g.A = P.agg; g.lda = (int)d; g.B = a->gine_lin0.weight; g.ldb = (int)d; g.C = P.h1; g.ldc = (int)d;
     g.bias = a->gine_lin0.bias; g.act = act; g.C_pre = P.h1_pre; g.ldpre = (int)d; g.precision = a->precision;
     set_bpk(g, P.pk_g0, d, d, 0);
+    g.Ap = P.agg_p; g.Bp = P.g0_p; g.Cp = P.h1_p;
     GPS_TRY(gemm(g, st));
     GemmParams g2;  // x_loc = x + drop(h1 W1^T + b1)  (gps_layer.py:188-189)
     g2.M = (int)N; g2.N = (int)d; g2.K = (int)d;
@@ -635,6 +773,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g2.offset_dev = (const unsigned long long*)a->offset_dev;
     g2.precision = a->precision;
     set_bpk(g2, P.pk_g1, d, d, 0);
+    g2.Ap = P.h1_p; g2.Bp = P.g1_p;
     GPS_TRY(gemm(g2, st));
   } else if (P.gcn) {
     // x_loc = x + drop(GCNConv(x))  (gps_layer.py:49-51,186-189); Y = x W^T is column block 0 of Y1
@@ -646,7 +785,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
   if (P.attn) {
     const float* Q = P.Y1 + P.qkv_off;
     GPS_TRY(attention_fwd(a->graph, P.H, P.hd, Q, Q + d, Q + 2 * d, P.Wy, P.O, d, P.lse, pa, a->seed, a->offset, sg,
-                          (const unsigned long long*)a->offset_dev));
+                          (const unsigned long long*)a->offset_dev, P.O_p));
     GemmParams g;  // hA = x + drop(O Wo^T + bo)
     g.M = (int)N; g.N = (int)d; g.K = (int)d;
     g.A = P.O; g.lda = (int)d; g.B = a->attn_out.weight; g.ldb = (int)d; g.C = P.hA; g.ldc = (int)d;
@@ -655,7 +794,8 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.offset_dev = (const unsigned long long*)a->offset_dev;
     g.precision = a->precision;
     set_bpk(g, P.pk_out, d, d, 0);
-    if (P.prepack && sp != st) GPS_TRY(sd->order(sp, sg));
+    g.Ap = P.O_p; g.Bp = P.out_p;
+    if (P.prepack && !P.use_planes && sp != st) GPS_TRY(sd->order(sp, sg));
     GPS_TRY(gemm(g, sg));
   }
 
@@ -669,6 +809,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
       g.M = (int)N; g.N = (int)inner; g.K = (int)d;
       g.A = a->x; g.lda = (int)d; g.B = lin[i]->weight; g.ldb = (int)d; g.C = dst[i]; g.ldc = (int)inner;
       g.precision = a->precision;
+      g.Ap = P.x_p; g.Bp = i == 0 ? P.pq_p : (i == 1 ? P.pk_p : P.pv_p);
       GPS_TRY(gemm(g, sg));
     }
     GPS_TRY(perf_prep(a->perf_proj, P.m, P.pPn, a->graph, P.H, P.pnmax, P.pgmax, P.pargk, sg));
@@ -707,12 +848,12 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     BnView bf = loc ? bn_view_fwd(P, a, BN_L, a->norm1_local, N) : bn_view_fwd(P, a, BN_A, a->norm1_attn, N);
     const float* second = (loc && (P.attn || P.perf)) ? P.hA : nullptr;
     BnView bs = bn_view_fwd(P, a, BN_A, a->norm1_attn, N);
-    GPS_TRY(bn_combine(first, bf, second, bs, P.s, N, d, st));
+    GPS_TRY(bn_combine(first, bf, second, bs, P.s, N, d, st, P.s_p));
   }
 
   // ---- FFN: t = s + drop(W2 drop(act(W1 s + b1)) + b2)   (gps_layer.py:225, 253-257)
   {
-    if (P.prepack && sp != st) GPS_TRY(sd->order(sp, st));
+    if (P.prepack && !P.use_planes && sp != st) GPS_TRY(sd->order(sp, st));
     GemmParams g;
     g.M = (int)N; g.N = (int)(2 * d); g.K = (int)d;
     g.A = P.s; g.lda = (int)d; g.B = a->ff1.weight; g.ldb = (int)d; g.C = P.hid; g.ldc = (int)(2 * d);
@@ -720,6 +861,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g.p_drop = pd; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_FF1; g.precision = a->precision;
     g.offset_dev = (const unsigned long long*)a->offset_dev;
     set_bpk(g, P.pk_ff1, 2 * d, d, 0);
+    g.Ap = P.s_p; g.Bp = P.ff1_p; g.Cp = P.hid_p;
     GPS_TRY(gemm(g, st));
     GemmParams g2;
     g2.M = (int)N; g2.N = (int)d; g2.K = (int)(2 * d);
@@ -728,6 +870,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     g2.p_drop = pd; g2.seed = a->seed; g2.offset = a->offset; g2.site = GPS_SITE_FF2; g2.precision = a->precision;
     g2.offset_dev = (const unsigned long long*)a->offset_dev;
     set_bpk(g2, P.pk_ff2, d, 2 * d, 0);
+    g2.Ap = P.hid_p; g2.Bp = P.ff2_p;
     GPS_TRY(gemm(g2, st));
     GPS_TRY(bn_combine(P.t, bn_view_fwd(P, a, BN_2, a->norm2, N), nullptr, BnView(), a->x_out, N, d, st));  // :229
   }
@@ -737,7 +880,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
 // =================================================================================== backward
 // out = a * dropout_scale(site)  (only launched when p > 0)
 static int dropmul(const float* src, float* dst, int64_t rows, int64_t d, const Plan& P, const GpsLayerArgs* a,
-                   int site, cudaStream_t st, float p2 = 0.f, int site2 = 0);
+                   int site, cudaStream_t st, float p2 = 0.f, int site2 = 0, Planes dstp = Planes());
 
 static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   Plan P;
@@ -781,6 +924,11 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     w.C = P.gWcat + r0 * d; w.ldc = (int)d;
     w.splitk = splitk_for(N, rows, d) < 2 ? 2 : splitk_for(N, rows, d);
     w.colsum_a = P.gbcat + r0; w.precision = prec;
+    w.Ap = P.gY1_p.cols(r0); w.Bp = P.x_p;
+    if (prec == GPS_PREC_BF16 && w.Ap.hi && N > 0) {
+      w.colsum_a = nullptr;
+      GPS_TRY(colsum(P.gY1 + r0, P.Wy, N, rows, P.gbcat + r0, s2));
+    }
     return N > 0 ? gemm(w, s2) : GPS_OK;
   };
 
@@ -818,13 +966,15 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   BnView v2 = bn_view(P, BN_2, a->norm2);
   GPS_TRY(bn_bwd_reduce(a->grad_x_out, d, P.t, d, N, d, v2, -1, nodrop, sums(BN_2), st));
   GPS_TRY(bn_bwd_apply(a->grad_x_out, d, P.t, d, N, d, v2, -1, nodrop, sums(BN_2), P.g_t, d, a->norm2.grad_weight,
-                       a->norm2.grad_bias, st, g_grads_accumulate));
+                       a->norm2.grad_bias, st, g_grads_accumulate, P.gt_p));
 
   // ---- FFN (gps_layer.py:253-257)
   const float* g_ff2 = P.g_t;  // gradient at the output of ff_linear2 (after ff_dropout2)
+  Planes g_ff2_p = P.gt_p;
   if (pd > 0.f) {
-    GPS_TRY(dropmul(P.g_t, P.g_tmp, N, d, P, a, GPS_SITE_FF2, st));
+    GPS_TRY(dropmul(P.g_t, P.g_tmp, N, d, P, a, GPS_SITE_FF2, st, 0.f, 0, P.gtmp_p));
     g_ff2 = P.g_tmp;
+    g_ff2_p = P.gtmp_p;
   }
   {
     GemmParams g;  // g_hid = (g_ff2 W2) * act'(pre) * drop1
@@ -835,15 +985,17 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g.p_drop = pd; g.seed = a->seed; g.offset = a->offset; g.site = GPS_SITE_FF1; g.precision = prec;
     g.offset_dev = (const unsigned long long*)a->offset_dev;
     set_bpt(g, P.pt_ff2, 2 * d, d);
+    g.Ap = g_ff2_p; g.Bp = P.ff2_p; g.Cp = P.ghid_p;
     GPS_TRY(gemm(g, st));
     GPS_TRY(wfork(st));
-    GPS_TRY(linear_wgrad(g_ff2, d, P.hid, 2 * d, N, d, 2 * d, a->ff2.grad_weight, a->ff2.grad_bias, prec, s2));
-    GPS_TRY(linear_wgrad(P.g_hid, 2 * d, P.s, d, N, 2 * d, d, a->ff1.grad_weight, a->ff1.grad_bias, prec, s2));
+    GPS_TRY(linear_wgrad(g_ff2, d, P.hid, 2 * d, N, d, 2 * d, a->ff2.grad_weight, a->ff2.grad_bias, prec, s2, g_ff2_p, P.hid_p));
+    GPS_TRY(linear_wgrad(P.g_hid, 2 * d, P.s, d, N, 2 * d, d, a->ff1.grad_weight, a->ff1.grad_bias, prec, s2, P.ghid_p, P.s_p));
     GemmParams g2;  // g_s = g_t + g_hid W1
     g2.M = (int)N; g2.N = (int)d; g2.K = (int)(2 * d);
     g2.A = P.g_hid; g2.lda = (int)(2 * d); g2.B = a->ff1.weight; g2.ldb = (int)d; g2.tb = 1; g2.C = P.g_s; g2.ldc = (int)d;
     g2.R1 = P.g_t; g2.ldr1 = (int)d; g2.precision = prec;
     set_bpt(g2, P.pt_ff1, d, 2 * d);
+    g2.Ap = P.ghid_p; g2.Bp = P.ff1_p;
     GPS_TRY(gemm(g2, st));
   }
 
@@ -853,32 +1005,36 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     BnView v = bn_view(P, BN_L, a->norm1_local);
     GPS_TRY(bn_bwd_reduce(P.g_s, d, P.xloc, d, N, d, v, -1, nodrop, sums(BN_L), st));
     GPS_TRY(bn_bwd_apply(P.g_s, d, P.xloc, d, N, d, v, -1, nodrop, sums(BN_L), P.g_xloc, d,
-                         a->norm1_local.grad_weight, a->norm1_local.grad_bias, st, g_grads_accumulate));
+                         a->norm1_local.grad_weight, a->norm1_local.grad_bias, st, g_grads_accumulate, P.gl1_p));
   }
   if (two_branches && sd) GPS_TRY(sd->order(st, sa));   // attention-branch backward runs next to the local-model backward
   if (P.attn) {
     BnView v = bn_view(P, BN_A, a->norm1_attn);
     GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), sa));
     GPS_TRY(bn_bwd_apply(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), P.g_hA, d, a->norm1_attn.grad_weight,
-                         a->norm1_attn.grad_bias, sa, g_grads_accumulate));
+                         a->norm1_attn.grad_bias, sa, g_grads_accumulate, P.ghA_p));
     // hA = x + drop(O Wo^T + bo)
     const float* g_ao = P.g_hA;
+    Planes g_ao_p = P.ghA_p;
     if (pd > 0.f) {
-      GPS_TRY(dropmul(P.g_hA, P.g_tmp2, N, d, P, a, GPS_SITE_ATTN_OUT, sa));
+      GPS_TRY(dropmul(P.g_hA, P.g_tmp2, N, d, P, a, GPS_SITE_ATTN_OUT, sa, 0.f, 0, P.gtmp2_p));
       g_ao = P.g_tmp2;
+      g_ao_p = P.gtmp2_p;
     }
     GemmParams g;  // g_O = g_ao Wo
     g.M = (int)N; g.N = (int)d; g.K = (int)d;
     g.A = g_ao; g.lda = (int)d; g.B = a->attn_out.weight; g.ldb = (int)d; g.tb = 1; g.C = P.g_O; g.ldc = (int)d;
     g.precision = prec;
     set_bpt(g, P.pt_out, d, d);
+    g.Ap = g_ao_p; g.Bp = P.out_p;
     GPS_TRY(gemm(g, sa));
     GPS_TRY(wfork(sa));
-    GPS_TRY(linear_wgrad(g_ao, d, P.O, d, N, d, d, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, s2));
+    GPS_TRY(linear_wgrad(g_ao, d, P.O, d, N, d, d, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, s2, g_ao_p, P.O_p));
     const float* Q = P.Y1 + P.qkv_off;
     float* gQ = P.gY1 + P.qkv_off;
     GPS_TRY(attention_bwd(a->graph, P.H, P.hd, Q, Q + d, Q + 2 * d, P.Wy, P.O, P.g_O, d, P.lse, P.delta, gQ, gQ + d,
-                          gQ + 2 * d, P.Wy, pa, a->seed, a->offset, sa, (const unsigned long long*)a->offset_dev));
+                          gQ + 2 * d, P.Wy, pa, a->seed, a->offset, sa, (const unsigned long long*)a->offset_dev,
+                          P.gY1_p.cols(P.qkv_off), P.gY1_p.cols(P.qkv_off + d), P.gY1_p.cols(P.qkv_off + 2 * d)));
   }
 
   if (P.perf) {
@@ -939,21 +1095,24 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     BnView vx = bn_view(P, BN_X, a->bn_node_x);
     GPS_TRY(bn_bwd_reduce(P.g_xloc, d, P.xt, d, N, d, vx, act, drop(GPS_SITE_GCN_X), sums(BN_X), st));
     GPS_TRY(bn_bwd_apply(P.g_xloc, d, P.xt, d, N, d, vx, act, drop(GPS_SITE_GCN_X), sums(BN_X), P.gY1, P.Wy,
-                         a->bn_node_x.grad_weight, a->bn_node_x.grad_bias, st, g_grads_accumulate));
+                         a->bn_node_x.grad_weight, a->bn_node_x.grad_bias, st, g_grads_accumulate, P.gY1_p));
     if (!early_edge) GPS_TRY(edge_bn_bwd());
     if (se != st) GPS_TRY(sd->order(se, st));
     // message/aggregate backward
-    GPS_TRY(gatedgcn_bwd_dst(a->graph, d, P.gY1, P.Wy, P.ehat, P.Y1 + d, P.Wy, P.g_e, P.g_num, P.gY1 + 2 * d, st));
-    GPS_TRY(gatedgcn_bwd_src(a->graph, d, P.g_e, P.ehat, P.g_num, P.gY1 + 3 * d, P.gY1 + d, P.Wy, st));
+    GPS_TRY(gatedgcn_bwd_dst(a->graph, d, P.gY1, P.Wy, P.ehat, P.Y1 + d, P.Wy, P.g_e, P.g_num, P.gY1 + 2 * d, st, P.ge_p,
+                             P.gY1_p.cols(2 * d)));
+    GPS_TRY(gatedgcn_bwd_src(a->graph, d, P.g_e, P.ehat, P.g_num, P.gY1 + 3 * d, P.gY1 + d, P.Wy, st, P.gY1_p.cols(3 * d),
+                             P.gY1_p.cols(d)));
     // C: dC = g_e^T e ; g_edge_attr = grad_edge_out + g_e C
     GPS_TRY(wfork(st));
-    GPS_TRY(linear_wgrad(P.g_e, d, a->edge_attr, d, E, d, d, a->gcn_C.grad_weight, a->gcn_C.grad_bias, prec, s2));
+    GPS_TRY(linear_wgrad(P.g_e, d, a->edge_attr, d, E, d, d, a->gcn_C.grad_weight, a->gcn_C.grad_bias, prec, s2, P.ge_p, P.e_p));
     if (a->grad_edge_attr && E > 0) {
       GemmParams g;
       g.M = (int)E; g.N = (int)d; g.K = (int)d;
       g.A = P.g_e; g.lda = (int)d; g.B = a->gcn_C.weight; g.ldb = (int)d; g.tb = 1; g.C = a->grad_edge_attr; g.ldc = (int)d;
       g.R1 = a->grad_edge_out; g.ldr1 = (int)d; g.precision = prec;
       set_bpt(g, P.pt_C, d, d);
+      g.Ap = P.ge_p; g.Bp = P.C_p;
       GPS_TRY(gemm(g, st));
     }
     if (split_tail) {
@@ -965,15 +1124,18 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
       g.A = P.gY1; g.lda = (int)P.Wy; g.B = P.Wcat; g.ldb = (int)d; g.tb = 1; g.C = a->grad_x; g.ldc = (int)d;
       g.R1 = P.g_xloc; g.ldr1 = (int)d; g.precision = prec;
       set_bpt(g, P.pt_cat, d, P.Wy);
+      g.Ap = P.gY1_p; g.Bp = P.Wcat_p;
       GPS_TRY(gemm(g, st));
     }
     g_x_local = P.g_xloc;  // residual x_in + ...
   } else if (P.gine) {
     // x_loc = x + drop(h1 W1^T + b1)
     const float* g_l1 = P.g_xloc;
+    Planes g_l1_p = P.gl1_p;
     if (pd > 0.f) {
-      GPS_TRY(dropmul(P.g_xloc, P.g_tmp3, N, d, P, a, GPS_SITE_LOCAL, st));
+      GPS_TRY(dropmul(P.g_xloc, P.g_tmp3, N, d, P, a, GPS_SITE_LOCAL, st, 0.f, 0, P.gtmp3_p));
       g_l1 = P.g_tmp3;
+      g_l1_p = P.gtmp3_p;
     }
     GemmParams g;  // g_h1 = (g_l1 W1) * act'(pre)
     g.M = (int)N; g.N = (int)d; g.K = (int)d;
@@ -981,15 +1143,17 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     if (relu) { g.mask_src = P.h1; g.mask_is_post = 1; } else { g.mask_src = P.h1_pre; g.mask_act = act; }
     g.ldmask = (int)d; g.precision = prec;
     set_bpt(g, P.pt_g1, d, d);
+    g.Ap = g_l1_p; g.Bp = P.g1_p; g.Cp = P.gh1_p;
     GPS_TRY(gemm(g, st));
     GPS_TRY(wfork(st));
-    GPS_TRY(linear_wgrad(g_l1, d, P.h1, d, N, d, d, a->gine_lin1.grad_weight, a->gine_lin1.grad_bias, prec, s2));
-    GPS_TRY(linear_wgrad(P.g_h1, d, P.agg, d, N, d, d, a->gine_lin0.grad_weight, a->gine_lin0.grad_bias, prec, s2));
+    GPS_TRY(linear_wgrad(g_l1, d, P.h1, d, N, d, d, a->gine_lin1.grad_weight, a->gine_lin1.grad_bias, prec, s2, g_l1_p, P.h1_p));
+    GPS_TRY(linear_wgrad(P.g_h1, d, P.agg, d, N, d, d, a->gine_lin0.grad_weight, a->gine_lin0.grad_bias, prec, s2, P.gh1_p, P.agg_p));
     GemmParams g2;  // g_agg = g_h1 W0
     g2.M = (int)N; g2.N = (int)d; g2.K = (int)d;
     g2.A = P.g_h1; g2.lda = (int)d; g2.B = a->gine_lin0.weight; g2.ldb = (int)d; g2.tb = 1; g2.C = P.g_agg; g2.ldc = (int)d;
     g2.precision = prec;
     set_bpt(g2, P.pt_g0, d, d);
+    g2.Ap = P.gh1_p; g2.Bp = P.g0_p;
     GPS_TRY(gemm(g2, st));
     GPS_REQUIRE(a->grad_edge_attr || E == 0, GPS_ERR_ARG, "grad_edge_attr is required for GINE");
     GPS_TRY(gine_bwd_dst(a->graph, d, a->x, a->edge_attr, P.g_agg, a->grad_edge_attr, st));
@@ -1006,7 +1170,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
       if (!g_grads_prezeroed) GPS_CUDA(cudaMemsetAsync(a->gcn_conv.grad_bias, 0, (size_t)d * sizeof(float), st));
       GPS_TRY(colsum(g_h, d, N, d, a->gcn_conv.grad_bias, st));
     }
-    GPS_TRY(gcn_bwd(a->graph, d, g_h, P.dinv, P.gY1, P.Wy, st));
+    GPS_TRY(gcn_bwd(a->graph, d, g_h, P.dinv, P.gY1, P.Wy, st, P.gY1_p));
     g_x_local = P.g_xloc;
   }
 
@@ -1029,6 +1193,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
       set_bpt(g, P.pt_cat, d, P.Wy);
       g.bpk_kb0 = (int)(wl / 64);
     }
+    g.Ap = P.gY1_p.cols(wl); g.Bp = P.Wcat_p.rows(wl);
     GPS_TRY(gemm(g, st));
   } else if (P.Wy) {
     GPS_TRY(wfork(st));
@@ -1038,6 +1203,11 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     w.A = P.gY1; w.lda = (int)P.Wy; w.ta = 1; w.B = a->x; w.ldb = (int)d; w.tb = 1; w.C = P.gWcat; w.ldc = (int)d;
     w.splitk = splitk_for(N, P.Wy, d) < 2 ? 2 : splitk_for(N, P.Wy, d);
     w.colsum_a = P.gbcat; w.precision = prec;
+    w.Ap = P.gY1_p; w.Bp = P.x_p;
+    if (prec == GPS_PREC_BF16 && w.Ap.hi && N > 0) {   // exact bias gradients in bf16 mode (see linear_wgrad)
+      w.colsum_a = nullptr;
+      GPS_TRY(colsum(P.gY1, P.Wy, N, P.Wy, P.gbcat, s2));
+    }
     if (N > 0) GPS_TRY(gemm(w, s2));
     PackDesc pdsc = pack_desc(a, P);
     k_unpack<<<(unsigned)pdsc.total_rows, 128, 0, s2>>>(pdsc, P.gWcat, P.gbcat, g_grads_accumulate ? 1 : 0);
@@ -1053,6 +1223,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
       g.splitk = 4;
     }
     set_bpt(g, P.pt_cat, d, P.Wy);
+    g.Ap = P.gY1_p; g.Bp = P.Wcat_p;
     GPS_TRY(gemm(g, st));
   } else if (g_x_local) {
     GPS_TRY(add3(g_x_local, d, P.perf ? P.g_xp : nullptr, d, nullptr, 0, a->grad_x, d, N, d, st));
@@ -1068,13 +1239,14 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
 namespace {
 __global__ void k_dropmul(const float* __restrict__ src, float* __restrict__ dst, int64_t n4, int64_t c4n, float p,
                           uint64_t seed, uint64_t offset, int site, const unsigned long long* offset_dev, float p2,
-                          int site2) {
+                          int site2, Planes dstp) {
   if (offset_dev) offset += *offset_dev;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 v = ld4(src + i * 4);
     if (p > 0.f) v = f4mul(v, dropout_scale4(p, seed, offset, site, (uint64_t)i));
     if (p2 > 0.f) v = f4mul(v, dropout_scale4(p2, seed, offset, site2, (uint64_t)i));
     st4(dst + i * 4, v);
+    if (dstp.hi) planes_store4(dstp, i / c4n, (i % c4n) * 4, v);
   }
 }
 __global__ void k_dropmask(float* __restrict__ dst, int64_t n4, float p, uint64_t seed, uint64_t offset, int site) {
@@ -1087,13 +1259,13 @@ __global__ void k_dropmask(float* __restrict__ dst, int64_t n4, float p, uint64_
 }  // namespace
 
 static int dropmul(const float* src, float* dst, int64_t rows, int64_t d, const Plan&, const GpsLayerArgs* a, int site,
-                   cudaStream_t st, float p2, int site2) {
+                   cudaStream_t st, float p2, int site2, Planes dstp) {
   int64_t n4 = rows * d / 4;
   if (n4 == 0) return GPS_OK;
   k_dropmul<<<(unsigned)std::min<int64_t>(ceil_div(n4, 256), kNumSMs * 8), 256, 0, st>>>(src, dst, n4, d / 4, a->dropout,
                                                                                         a->seed, a->offset, site,
                                                                                         (const unsigned long long*)a->offset_dev,
-                                                                                        p2, site2);
+                                                                                        p2, site2, dstp);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }
@@ -1107,6 +1279,30 @@ extern "C" const char* gps_last_error(void) { return g_err; }
 extern "C" int gps_abi_version(void) { return GPS_ABI_VERSION; }
 extern "C" const char* gps_build_arch(void) { return "sm_100a"; }
 extern "C" unsigned long long gps_launch_count(void) { return g_launches.load(); }
+extern "C" unsigned long long gps_fallback_count(void) { return g_fallbacks.load(); }
+
+extern "C" int gps_to_planes(const float* src, int64_t ld, int64_t rows, int64_t cols, void* hi, void* lo, int64_t ldp,
+                             void* stream) {
+  GPS_REQUIRE(src && hi, GPS_ERR_ARG, "gps_to_planes: null argument");
+  ToPlanesItem it{src, ld, (int)rows, (int)cols, Planes{(__nv_bfloat16*)hi, (__nv_bfloat16*)lo, ldp}};
+  return to_planes(&it, 1, (cudaStream_t)stream);
+}
+
+extern "C" int gps_gemm_planes(const void* A_hi, const void* A_lo, int64_t lda, int32_t ta, const void* B_hi,
+                               const void* B_lo, int64_t ldb, int32_t tb, float* C, int64_t ldc, void* C_hi, void* C_lo,
+                               int64_t ldcp, int64_t M, int64_t N, int64_t K, int32_t splitk, int32_t precision,
+                               float* colsum_a, void* stream) {
+  GemmParams g;
+  g.M = (int)M; g.N = (int)N; g.K = (int)K;
+  g.ta = ta; g.tb = tb; g.C = C; g.ldc = (int)ldc;
+  g.Ap = Planes{(__nv_bfloat16*)A_hi, (__nv_bfloat16*)A_lo, lda};
+  g.Bp = Planes{(__nv_bfloat16*)B_hi, (__nv_bfloat16*)B_lo, ldb};
+  g.Cp = Planes{(__nv_bfloat16*)C_hi, (__nv_bfloat16*)C_lo, ldcp};
+  g.splitk = splitk < 1 ? 1 : splitk; g.precision = precision; g.colsum_a = colsum_a;
+  int rc = gemm_tma(g, (cudaStream_t)stream);
+  if (rc == GPS_ERR_UNSUPPORTED) set_error("gps_gemm_planes: the TMA kernel does not take this shape/alignment");
+  return rc;
+}
 extern "C" void gps_debug_set(int v) { gemm_tc_set_debug(v); }
 
 extern "C" int gps_layer_plan(const GpsLayerArgs* args, GpsLayerPlan* plan) {

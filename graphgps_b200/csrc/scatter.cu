@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(1024) k_gatedgcn_fwd(GpsGraph g, int d, const 
 __global__ void k_gatedgcn_bwd_dst(GpsGraph g, int d, const float* __restrict__ g_xt, int64_t ldg,
                                    const float* __restrict__ ehat, const float* __restrict__ Bx, int64_t ldy,
                                    float* __restrict__ g_e, float* __restrict__ g_num,
-                                   float* __restrict__ g_Dx) {
+                                   float* __restrict__ g_Dx, Planes g_e_p, Planes g_Dx_p) {
   const int c = threadIdx.x * 4, ry = threadIdx.y, RY = blockDim.y;
   for (int64_t i = (int64_t)blockIdx.x * RY + ry; i < g.N; i += (int64_t)gridDim.x * RY) {
     const int kb = g.dst_ptr[i], ke = g.dst_ptr[i + 1];
@@ -167,15 +167,18 @@ __global__ void k_gatedgcn_bwd_dst(GpsGraph g, int d, const float* __restrict__ 
       ge.z += gs.z * s.z * (1.f - s.z);
       ge.w += gs.w * s.w * (1.f - s.w);
       st4(g_e + eid * d + c, ge);
+      if (g_e_p.hi) planes_store4(g_e_p, eid, c, ge);
       gdx = f4add(gdx, ge);
     }
     st4(g_Dx + i * ldg + c, gdx);
+    if (g_Dx_p.hi) planes_store4(g_Dx_p, i, c, gdx);
   }
 }
 
 __global__ void k_gatedgcn_bwd_src(GpsGraph g, int d, const float* __restrict__ g_e,
                                    const float* __restrict__ ehat, const float* __restrict__ g_num,
-                                   float* __restrict__ g_Ex, float* __restrict__ g_Bx, int64_t ldg) {
+                                   float* __restrict__ g_Ex, float* __restrict__ g_Bx, int64_t ldg, Planes g_Ex_p,
+                                   Planes g_Bx_p) {
   const int c = threadIdx.x * 4, ry = threadIdx.y, RY = blockDim.y;
   for (int64_t j = (int64_t)blockIdx.x * RY + ry; j < g.N; j += (int64_t)gridDim.x * RY) {
     float4 gex = f4zero(), gbx = f4zero();
@@ -189,11 +192,13 @@ __global__ void k_gatedgcn_bwd_src(GpsGraph g, int d, const float* __restrict__ 
     }
     st4(g_Ex + j * ldg + c, gex);
     st4(g_Bx + j * ldg + c, gbx);
+    if (g_Ex_p.hi) planes_store4(g_Ex_p, j, c, gex);
+    if (g_Bx_p.hi) planes_store4(g_Bx_p, j, c, gbx);
   }
 }
 
 __global__ void k_gine_fwd(GpsGraph g, int d, const float* __restrict__ x, const float* __restrict__ e,
-                           float eps, float* __restrict__ out) {
+                           float eps, float* __restrict__ out, Planes outp) {
   const int c = threadIdx.x * 4, ry = threadIdx.y, RY = blockDim.y;
   for (int64_t i = (int64_t)blockIdx.x * RY + ry; i < g.N; i += (int64_t)gridDim.x * RY) {
     float4 acc = f4scale(ld4(x + i * d + c), 1.f + eps);
@@ -208,6 +213,7 @@ __global__ void k_gine_fwd(GpsGraph g, int d, const float* __restrict__ x, const
       acc.w += fmaxf(m.w, 0.f);
     }
     st4(out + i * d + c, acc);
+    if (outp.hi) planes_store4(outp, i, c, acc);
   }
 }
 
@@ -284,7 +290,7 @@ __global__ void __launch_bounds__(1024) k_gcn_fwd(GpsGraph g, int d, const float
 
 // gY_j = dinv_j (dinv_j g_h_j + sum_{j->i, i != j} dinv_i g_h_i)   (the adjoint of the aggregation above)
 __global__ void k_gcn_bwd(GpsGraph g, int d, const float* __restrict__ g_h, const float* __restrict__ dinv,
-                          float* __restrict__ gY, int64_t ldg) {
+                          float* __restrict__ gY, int64_t ldg, Planes gYp) {
   const int c = threadIdx.x * 4, ry = threadIdx.y, RY = blockDim.y;
   for (int64_t j = (int64_t)blockIdx.x * RY + ry; j < g.N; j += (int64_t)gridDim.x * RY) {
     const float dj = dinv[j];
@@ -295,6 +301,7 @@ __global__ void k_gcn_bwd(GpsGraph g, int d, const float* __restrict__ g_h, cons
       a = f4fma(make_float4(dinv[i], dinv[i], dinv[i], dinv[i]), ld4(g_h + (int64_t)i * d + c), a);
     }
     st4(gY + j * ldg + c, f4scale(a, dj));
+    if (gYp.hi) planes_store4(gYp, j, c, f4scale(a, dj));
   }
 }
 
@@ -321,11 +328,11 @@ int gcn_fwd(const GpsGraph& g, int64_t d, const float* Y, int64_t ldy, const flo
 }
 
 int gcn_bwd(const GpsGraph& g, int64_t d, const float* g_h, const float* dinv, float* gY, int64_t ldg,
-            cudaStream_t stream) {
+            cudaStream_t stream, Planes gYp) {
   if (g.N == 0) return GPS_OK;
   NodeGeom ng;
   GPS_TRY(node_geom(g.N, d, 0, &ng));
-  k_gcn_bwd<<<ng.grid, ng.block, 0, stream>>>(g, (int)d, g_h, dinv, gY, ldg);
+  k_gcn_bwd<<<ng.grid, ng.block, 0, stream>>>(g, (int)d, g_h, dinv, gY, ldg, gYp);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }
@@ -346,31 +353,31 @@ int gatedgcn_fwd(const GpsGraph& g, int64_t d, const float* Ax, const float* Bx,
 }
 
 int gatedgcn_bwd_dst(const GpsGraph& g, int64_t d, const float* g_xt, int64_t ldg, const float* ehat, const float* Bx,
-                     int64_t ldy, float* g_e, float* g_num, float* g_Dx, cudaStream_t stream) {
+                     int64_t ldy, float* g_e, float* g_num, float* g_Dx, cudaStream_t stream, Planes g_e_p, Planes g_Dx_p) {
   if (g.N == 0) return GPS_OK;
   NodeGeom ng;
   GPS_TRY(node_geom(g.N, d, 0, &ng));
-  k_gatedgcn_bwd_dst<<<ng.grid, ng.block, 0, stream>>>(g, (int)d, g_xt, ldg, ehat, Bx, ldy, g_e, g_num, g_Dx);
+  k_gatedgcn_bwd_dst<<<ng.grid, ng.block, 0, stream>>>(g, (int)d, g_xt, ldg, ehat, Bx, ldy, g_e, g_num, g_Dx, g_e_p, g_Dx_p);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }
 
 int gatedgcn_bwd_src(const GpsGraph& g, int64_t d, const float* g_e, const float* ehat, const float* g_num,
-                     float* g_Ex, float* g_Bx, int64_t ldg, cudaStream_t stream) {
+                     float* g_Ex, float* g_Bx, int64_t ldg, cudaStream_t stream, Planes g_Ex_p, Planes g_Bx_p) {
   if (g.N == 0) return GPS_OK;
   NodeGeom ng;
   GPS_TRY(node_geom(g.N, d, 0, &ng));
-  k_gatedgcn_bwd_src<<<ng.grid, ng.block, 0, stream>>>(g, (int)d, g_e, ehat, g_num, g_Ex, g_Bx, ldg);
+  k_gatedgcn_bwd_src<<<ng.grid, ng.block, 0, stream>>>(g, (int)d, g_e, ehat, g_num, g_Ex, g_Bx, ldg, g_Ex_p, g_Bx_p);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }
 
 int gine_fwd(const GpsGraph& g, int64_t d, const float* x, const float* e, float eps, float* out,
-             cudaStream_t stream) {
+             cudaStream_t stream, Planes outp) {
   if (g.N == 0) return GPS_OK;
   NodeGeom ng;
   GPS_TRY(node_geom(g.N, d, 0, &ng));
-  k_gine_fwd<<<ng.grid, ng.block, 0, stream>>>(g, (int)d, x, e, eps, out);
+  k_gine_fwd<<<ng.grid, ng.block, 0, stream>>>(g, (int)d, x, e, eps, out, outp);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }

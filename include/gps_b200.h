@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define GPS_ABI_VERSION 2
+#define GPS_ABI_VERSION 3
 
 enum { GPS_OK = 0, GPS_ERR_ARG = -1, GPS_ERR_UNSUPPORTED = -2, GPS_ERR_CUDA = -3 };
 
@@ -222,6 +222,21 @@ int gps_attention_backward(const GpsGraph* g, int64_t heads, int64_t hd, const f
                            const float* dO, int64_t ldo, const float* lse, float* delta,
                            float* dQ, float* dK, float* dV, int64_t ldg, float p_drop,
                            uint64_t seed, uint64_t offset, void* stream);
+
+/* ABI 3: operand "planes" of the TMA-fed tcgen05 GEMM (csrc/gemm_tma.cu).  A plane pair is the bf16 image of an
+ * fp32 matrix: hi = bf16(v), lo = bf16(v - hi), both plain row-major with pitch ldp (elements, multiple of 8); lo may
+ * be NULL for GPS_PREC_BF16.  gps_to_planes converts; gps_gemm_planes multiplies plane operands stored as
+ * A: [M,K] (ta = 0) or [K,M] (ta = 1), B: [N,K] (tb = 0, an nn.Linear weight) or [K,N] (tb = 1), writes fp32 C
+ * (may be NULL) and/or the planes of C, optionally adds the row sums of Aop into colsum_a[M] (ta = 1: the bias
+ * gradient of dW = G^T X).  splitk > 1 accumulates atomically into a pre-zeroed fp32 C. */
+int gps_to_planes(const float* src, int64_t ld, int64_t rows, int64_t cols, void* hi, void* lo, int64_t ldp,
+                  void* stream);
+int gps_gemm_planes(const void* A_hi, const void* A_lo, int64_t lda, int32_t ta, const void* B_hi, const void* B_lo,
+                    int64_t ldb, int32_t tb, float* C, int64_t ldc, void* C_hi, void* C_lo, int64_t ldcp, int64_t M,
+                    int64_t N, int64_t K, int32_t splitk, int32_t precision, float* colsum_a, void* stream);
+/* number of dense products that fell back from the tensor-core kernels to the exact CUDA-core kernel
+ * (unaligned / odd shapes) in this process; with GPS_B200_STRICT=1 in the environment such a fallback is an error */
+unsigned long long gps_fallback_count(void);
 
 /* Dropout keep-mask generator used by every dropout site (tests replay it): writes 1/0 floats. */
 int gps_dropout_mask(float* mask, int64_t rows, int64_t cols, float p, uint64_t seed,
