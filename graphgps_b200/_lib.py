@@ -98,6 +98,7 @@ SYMBOLS = {
     # not in the header's stage list but part of the ABI: launch counter for bench.py
     "gps_launch_count": (C.c_ulonglong, []),
     "gps_debug_set": (None, [C.c_int]),
+    "gps_debug_tma": (None, [C.c_int, _fp]),
 }
 
 _lib = None

@@ -48,6 +48,7 @@ int to_planes(const ToPlanesItem* items, int n, cudaStream_t stream);
 // TMA-fed tcgen05 product on plane operands; GPS_ERR_UNSUPPORTED when the planes are missing / misaligned
 int gemm_tma(const GemmParams& p, cudaStream_t stream);
 void gemm_tma_set_force_bn(int bn);
+void gemm_tma_set_trace(unsigned long long* buf);   // bring-up: per-CTA phase timestamps (tools/gemm_trace.py)
 
 // Pre-packs up to 8 weight matrices (fp32 [rows, K] row-major) into the tcgen05 kernel's shared-memory tile image.
 // K-major (mn = 0): W is [rows x K], dst sized by prepack_bytes(rows, K).

@@ -44,7 +44,19 @@ constexpr int kBlock = 64 * BK * 2;     // 8 KB: one 64-column MN-major block / 
 struct TmaArgs {
   GemmParams p;
   int BN, nb_blocks, stages, kb_per_split, tmem_cols, planes;
+  int debug;                   // bring-up: 1 no global stores in the epilogue, 2 no TMEM loads
+  unsigned long long* trace;   // bring-up: 16 globaltimer stamps per CTA (first 256 CTAs), see tools/gemm_trace.py
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define GPS_TRACE(slot)                                                                         \
+  do {                                                                                          \
+    if (a.trace && cta_lin < 256) a.trace[cta_lin * 16 + (slot)] = gtimer();                    \
+  } while (0)
 
 template <bool A_MN, bool B_MN, bool NARROW>
 __global__ void __launch_bounds__(kThreads, NARROW ? 2 : 1)
@@ -67,8 +79,15 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   const int kb_end = min(nkb_total, kb_begin + a.kb_per_split);
   const int nkb = kb_end - kb_begin;
   const bool do_colsum = A_MN && p.colsum_a != nullptr && blockIdx.x == 0;
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
 
   if (tid == 0) {
+    GPS_TRACE(0);
+    if (a.trace && cta_lin < 256) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+      a.trace[cta_lin * 16 + 8] = smid;
+    }
     for (int s = 0; s < S; ++s) {
       mbar_init(smem_u32(&bars[s]), 1);
       mbar_init(smem_u32(&bars[S + s]), 1 + (do_colsum ? kEpiWarps : 0));
@@ -85,6 +104,7 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) GPS_TRACE(1);
 
   if (warp == kTmaWarp) {
     // =========================================================== TMA producer
@@ -116,7 +136,9 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             for (int b = 0; b < b_blocks; ++b) tma_tile_3d(sb + pl * b_tile + b * kBlock, &tmB, n0 + 64 * b, k0, pl, full);
           }
         }
+        if (i == 0) GPS_TRACE(2);
       }
+      GPS_TRACE(9);
     }
     __syncwarp();
   } else if (warp == kMmaWarp) {
@@ -129,6 +151,8 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const int s = i % S;
         mbar_wait(smem_u32(&bars[s]), (uint32_t)(i / S) & 1u);
         tc_fence_after();
+        if (i == 0) GPS_TRACE(3);
+        if (i == nkb - 1) GPS_TRACE(10);
         const uint32_t sa_hi = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t sb_hi = sa_hi + planes * kATile;
         const uint32_t sa_lo = sa_hi + kATile;
@@ -150,6 +174,7 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         umma_commit(smem_u32(&bars[S + s]));   // frees the smem stage once these MMAs retire
       }
       umma_commit(smem_u32(&bars[2 * S]));     // accumulator complete
+      GPS_TRACE(4);
     }
     __syncwarp();
   } else {
@@ -203,126 +228,186 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       __syncwarp();
       tc_fence_after();
     }
-    const int q = warp & 3, half = warp >> 2;
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    const int nchunks = a.BN >> 4;
-    const uint64_t drop_off = p.offset + ((p.p_drop > 0.f || p.p_drop2 > 0.f) && p.offset_dev ? *p.offset_dev : 0ull);
-    for (int c = half; c < nchunks; c += 2) {
-      const int gn = n0 + c * 16;
-      if (gn >= p.N) break;
-      float v[16];
-      if (nkb > 0) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), v);
-      else {
+    if (tid == 0) GPS_TRACE(5);
+    // ---- phase 1: accumulator TMEM -> registers -> shared staging tile [128][BN + 4] fp32.  All MMAs have retired, so
+    // the operand stages are free and double as the staging buffer.  The pad keeps both the row-per-lane writes here and
+    // the row-contiguous reads of phase 2 bank-conflict free.
+    float* stage = reinterpret_cast<float*>(smem);
+    const int sld = a.BN + 4;
+    {
+      const int q = warp & 3, half = warp >> 2;
+      const int r = q * 32 + lane;
+      const int nchunks = a.BN >> 4;
+      for (int c = half; c < nchunks; c += 2) {
+        float v[16];
+        if (nkb > 0 && !(a.debug & 2)) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16), v);
+        else {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = 0.f;
+          for (int e = 0; e < 16; ++e) v[e] = 0.f;
+        }
+        float4* dst = reinterpret_cast<float4*>(stage + r * sld + c * 16);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) dst[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
       }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    // ---- phase 2: G = BN/4 threads per row, each owning 4 consecutive columns for all of its rows: every global access
+    // (bias, residuals, act' mask, fp32 / plane stores, split-K atomics) is a contiguous row segment, the per-column
+    // constants live in registers and the BatchNorm column sums are accumulated per thread.
+    const int G = a.BN >> 2;
+    const int rpp = kEpiWarps * 32 / G;            // rows per pass
+    const int rip = tid / G, cg = tid - rip * G;
+    const int col = n0 + cg * 4;
+    const bool col_ok = rip < rpp && col < p.N;
+    float4 s1 = f4zero(), s2 = f4zero();
+    if (col_ok) {
+      // rows of this thread: r = rip + k * rpp, k < nrows.  Everything is addressed through per-thread base pointers
+      // advanced by a constant stride, and the loop is unrolled by 4 rows so that the shared/global loads of a group are
+      // in flight together: with 2 epilogue warps per scheduler the pass is instruction-latency bound otherwise
+      // (measured: 8.5 us for a 128 x 256 tile with neither the TMEM loads nor the global stores on the critical path).
+      const int rows_here = min(BM, p.M - m0);
+      const int nrows = rip < rows_here ? (rows_here - rip + rpp - 1) / rpp : 0;
+      const int64_t row0 = m0 + rip;
+      const float* sp = stage + rip * sld + cg * 4;
+      const int s_st = rpp * sld;
+      float* cp = p.C ? p.C + row0 * p.ldc + col : nullptr;
+      const int64_t c_st = (int64_t)rpp * p.ldc;
+      const float* r1 = p.R1 ? p.R1 + row0 * p.ldr1 + col : nullptr;
+      const int64_t r1_st = (int64_t)rpp * p.ldr1;
+      const float* r2 = p.R2 ? p.R2 + row0 * p.ldr2 + col : nullptr;
+      const int64_t r2_st = (int64_t)rpp * p.ldr2;
       if (p.splitk > 1) {
-        if (row_ok) {
-          float* dst = p.C + (int64_t)row * p.ldc + gn;
+        const bool res = blockIdx.z == 0;            // the first split also carries the residual terms
+        for (int k = 0; k < nrows; k += 4) {
+          float4 w[4];
 #pragma unroll
-          for (int e = 0; e < 16; e += 4) {   // N % 4 == 0: whole 16-byte groups; red.global.add.v4.f32
-            if (gn + e >= p.N) continue;
-            float4 w4 = make_float4(v[e], v[e + 1], v[e + 2], v[e + 3]);
-            if (blockIdx.z == 0) {            // the first split also carries the residual terms
-              if (p.R1) w4 = f4add(w4, ld4(p.R1 + (int64_t)row * p.ldr1 + gn + e));
-              if (p.R2) w4 = f4add(w4, ld4(p.R2 + (int64_t)row * p.ldr2 + gn + e));
+          for (int u = 0; u < 4; ++u) w[u] = k + u < nrows ? *reinterpret_cast<const float4*>(sp + (k + u) * s_st) : f4zero();
+          if (res && r1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (k + u < nrows) w[u] = f4add(w[u], ld4(r1 + (k + u) * r1_st));
+          }
+          if (res && r2) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (k + u < nrows) w[u] = f4add(w[u], ld4(r2 + (k + u) * r2_st));
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (k + u < nrows) atomicAdd(reinterpret_cast<float4*>(cp + (k + u) * c_st), w[u]);   // red.global.add.v4.f32
+        }
+      } else {
+        const bool fast = !p.C_pre && !(p.mask_src && !p.mask_is_post) && p.p_drop == 0.f && p.p_drop2 == 0.f &&
+                          (p.act < 0 || p.act == GPS_ACT_RELU);
+        const float4 bb = p.bias ? ld4(p.bias + col) : f4zero();
+        const float* mk = p.mask_src ? p.mask_src + row0 * p.ldmask + col : nullptr;
+        const int64_t mk_st = (int64_t)rpp * p.ldmask;
+        __nv_bfloat16* ph = p.Cp.hi ? p.Cp.hi + row0 * p.Cp.ld + col : nullptr;
+        __nv_bfloat16* pl = p.Cp.lo ? p.Cp.lo + row0 * p.Cp.ld + col : nullptr;
+        const int64_t p_st = (int64_t)rpp * p.Cp.ld;
+        const bool relu = p.act == GPS_ACT_RELU;
+        if (fast) {
+          for (int k = 0; k < nrows; k += 4) {
+            float4 w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              w[u] = f4add(k + u < nrows ? *reinterpret_cast<const float4*>(sp + (k + u) * s_st) : f4zero(), bb);
+            if (relu) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                w[u] = make_float4(fmaxf(w[u].x, 0.f), fmaxf(w[u].y, 0.f), fmaxf(w[u].z, 0.f), fmaxf(w[u].w, 0.f));
             }
-            atomicAdd(reinterpret_cast<float4*>(dst + e), w4);
+            if (mk) {   // relu': the saved post-activation value is positive
+              float4 m[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) m[u] = k + u < nrows ? ld4(mk + (k + u) * mk_st) : f4zero();
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                w[u] = make_float4(m[u].x > 0.f ? w[u].x : 0.f, m[u].y > 0.f ? w[u].y : 0.f, m[u].z > 0.f ? w[u].z : 0.f,
+                                   m[u].w > 0.f ? w[u].w : 0.f);
+            }
+            if (r1) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) if (k + u < nrows) w[u] = f4add(w[u], ld4(r1 + (k + u) * r1_st));
+            }
+            if (r2) {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) if (k + u < nrows) w[u] = f4add(w[u], ld4(r2 + (k + u) * r2_st));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (k + u >= nrows) continue;
+              if (cp && !(a.debug & 1)) st4(cp + (k + u) * c_st, w[u]);
+              if (ph) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(w[u].x, w[u].y), h1 = __floats2bfloat162_rn(w[u].z, w[u].w);
+                *reinterpret_cast<uint2*>(ph + (k + u) * p_st) =
+                    make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+                if (pl) {
+                  __nv_bfloat162 l0 = __floats2bfloat162_rn(w[u].x - __low2float(h0), w[u].y - __high2float(h0));
+                  __nv_bfloat162 l1 = __floats2bfloat162_rn(w[u].z - __low2float(h1), w[u].w - __high2float(h1));
+                  *reinterpret_cast<uint2*>(pl + (k + u) * p_st) =
+                      make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+                }
+              }
+              s1 = f4add(s1, w[u]);
+              s2 = f4fma(w[u], w[u], s2);
+            }
+          }
+        } else {
+          // general path: pre-activation copy, GELU and its derivative, dropout (two chained sites for the Performer)
+          const uint64_t drop_off = p.offset + ((p.p_drop > 0.f || p.p_drop2 > 0.f) && p.offset_dev ? *p.offset_dev : 0ull);
+          for (int k = 0; k < nrows; ++k) {
+            const int64_t row = row0 + (int64_t)k * rpp;
+            float4 w = f4add(*reinterpret_cast<const float4*>(sp + k * s_st), bb);
+            if (p.C_pre) st4(p.C_pre + row * p.ldpre + col, w);
+            if (p.act >= 0) w = make_float4(act_fwd_rt(p.act, w.x), act_fwd_rt(p.act, w.y), act_fwd_rt(p.act, w.z), act_fwd_rt(p.act, w.w));
+            if (mk) {
+              const float4 ms = ld4(mk + k * mk_st);
+              if (p.mask_is_post) {
+                w.x = ms.x > 0.f ? w.x : 0.f; w.y = ms.y > 0.f ? w.y : 0.f; w.z = ms.z > 0.f ? w.z : 0.f; w.w = ms.w > 0.f ? w.w : 0.f;
+              } else {
+                w.x *= act_bwd_rt(p.mask_act, ms.x); w.y *= act_bwd_rt(p.mask_act, ms.y);
+                w.z *= act_bwd_rt(p.mask_act, ms.z); w.w *= act_bwd_rt(p.mask_act, ms.w);
+              }
+            }
+            if (p.p_drop2 > 0.f) w = f4mul(w, dropout_scale4(p.p_drop2, p.seed, drop_off, p.site2, ((uint64_t)row * (uint64_t)p.N + col) >> 2));
+            if (p.p_drop > 0.f) w = f4mul(w, dropout_scale4(p.p_drop, p.seed, drop_off, p.site, ((uint64_t)row * (uint64_t)p.N + col) >> 2));
+            if (r1) w = f4add(w, ld4(r1 + k * r1_st));
+            if (r2) w = f4add(w, ld4(r2 + k * r2_st));
+            if (cp) st4(cp + k * c_st, w);
+            if (ph) planes_store4(p.Cp, row, col, w);
+            s1 = f4add(s1, w);
+            s2 = f4fma(w, w, s2);
           }
         }
-        continue;
       }
-#pragma unroll
-      for (int g4 = 0; g4 < 4; ++g4) {
-        const int col = gn + g4 * 4;
-        const bool ok = row_ok && col < p.N;
-        float* w = v + g4 * 4;
-        if (p.bias && col < p.N) {
-          float4 bb = ld4(p.bias + col);
-          w[0] += bb.x; w[1] += bb.y; w[2] += bb.z; w[3] += bb.w;
-        }
-        if (ok && p.C_pre) st4(p.C_pre + (int64_t)row * p.ldpre + col, make_float4(w[0], w[1], w[2], w[3]));
-        if (p.act >= 0) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) w[e] = act_fwd_rt(p.act, w[e]);
-        }
-        if (ok && p.mask_src) {
-          float4 ms = ld4(p.mask_src + (int64_t)row * p.ldmask + col);
-          float mv[4] = {ms.x, ms.y, ms.z, ms.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) w[e] *= p.mask_is_post ? (mv[e] > 0.f ? 1.f : 0.f) : act_bwd_rt(p.mask_act, mv[e]);
-        }
-        if (ok && p.p_drop2 > 0.f) {
-          float4 sc = dropout_scale4(p.p_drop2, p.seed, drop_off, p.site2, ((uint64_t)row * (uint64_t)p.N + col) >> 2);
-          w[0] *= sc.x; w[1] *= sc.y; w[2] *= sc.z; w[3] *= sc.w;
-        }
-        if (ok && p.p_drop > 0.f) {
-          float4 sc = dropout_scale4(p.p_drop, p.seed, drop_off, p.site, ((uint64_t)row * (uint64_t)p.N + col) >> 2);
-          w[0] *= sc.x; w[1] *= sc.y; w[2] *= sc.z; w[3] *= sc.w;
-        }
-        if (ok && p.R1) {
-          float4 r = ld4(p.R1 + (int64_t)row * p.ldr1 + col);
-          w[0] += r.x; w[1] += r.y; w[2] += r.z; w[3] += r.w;
-        }
-        if (ok && p.R2) {
-          float4 r = ld4(p.R2 + (int64_t)row * p.ldr2 + col);
-          w[0] += r.x; w[1] += r.y; w[2] += r.z; w[3] += r.w;
-        }
-        if (ok && p.C) st4(p.C + (int64_t)row * p.ldc + col, make_float4(w[0], w[1], w[2], w[3]));
-        if (ok && p.Cp.hi) planes_store4(p.Cp, row, col, make_float4(w[0], w[1], w[2], w[3]));
-        if (!ok) { w[0] = w[1] = w[2] = w[3] = 0.f; }
+    }
+    if (p.stats) {
+      // column sums: the rpp threads that share a column group meet in shared memory, one double atomic per column per CTA
+      float4* rs = reinterpret_cast<float4*>(red);
+      if (rip < rpp) {
+        rs[(rip * G + cg) * 2] = s1;
+        rs[(rip * G + cg) * 2 + 1] = s2;
       }
-      if (p.stats) {
-        // column sums over the warp's 32 rows: butterfly reduce-scatter, 16 columns x {sum, sumsq}
-        float s1[16], s2[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) { s1[e] = v[e]; s2[e] = v[e] * v[e]; }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const bool up = (lane & 16) != 0;
-          float send1 = up ? s1[e] : s1[e + 8], send2 = up ? s2[e] : s2[e + 8];
-          float keep1 = up ? s1[e + 8] : s1[e], keep2 = up ? s2[e + 8] : s2[e];
-          s1[e] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 16);
-          s2[e] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 16);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid < G && n0 + tid * 4 < p.N) {
+        float4 t1 = f4zero(), t2 = f4zero();
+        for (int y = 0; y < rpp; ++y) {
+          t1 = f4add(t1, rs[(y * G + tid) * 2]);
+          t2 = f4add(t2, rs[(y * G + tid) * 2 + 1]);
         }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const bool up = (lane & 8) != 0;
-          float send1 = up ? s1[e] : s1[e + 4], send2 = up ? s2[e] : s2[e + 4];
-          float keep1 = up ? s1[e + 4] : s1[e], keep2 = up ? s2[e + 4] : s2[e];
-          s1[e] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 8);
-          s2[e] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 8);
-        }
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const bool up = (lane & 4) != 0;
-          float send1 = up ? s1[e] : s1[e + 2], send2 = up ? s2[e] : s2[e + 2];
-          float keep1 = up ? s1[e + 2] : s1[e], keep2 = up ? s2[e + 2] : s2[e];
-          s1[e] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 4);
-          s2[e] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 4);
-        }
-        {
-          const bool up = (lane & 2) != 0;
-          float send1 = up ? s1[0] : s1[1], send2 = up ? s2[0] : s2[1];
-          float keep1 = up ? s1[1] : s1[0], keep2 = up ? s2[1] : s2[0];
-          s1[0] = keep1 + __shfl_xor_sync(0xffffffffu, send1, 2);
-          s2[0] = keep2 + __shfl_xor_sync(0xffffffffu, send2, 2);
-        }
-        s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
-        s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
-        const int colj = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-        if ((lane & 1) == 0 && gn + colj < p.N) {
-          atomic_add_f64(&p.stats[gn + colj], (double)s1[0]);
-          atomic_add_f64(&p.stats[(int64_t)p.N + gn + colj], (double)s2[0]);
-        }
+        const int c0 = n0 + tid * 4;
+        atomic_add_f64(&p.stats[c0 + 0], (double)t1.x); atomic_add_f64(&p.stats[c0 + 1], (double)t1.y);
+        atomic_add_f64(&p.stats[c0 + 2], (double)t1.z); atomic_add_f64(&p.stats[c0 + 3], (double)t1.w);
+        atomic_add_f64(&p.stats[(int64_t)p.N + c0 + 0], (double)t2.x); atomic_add_f64(&p.stats[(int64_t)p.N + c0 + 1], (double)t2.y);
+        atomic_add_f64(&p.stats[(int64_t)p.N + c0 + 2], (double)t2.z); atomic_add_f64(&p.stats[(int64_t)p.N + c0 + 3], (double)t2.w);
       }
     }
   }
 
+  if (tid == 0) GPS_TRACE(6);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (tid == 0) GPS_TRACE(7);
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
 }
 
@@ -411,10 +496,13 @@ int launch(const CUtensorMap& tA, const CUtensorMap& tB, const TmaArgs& a, dim3 
 }
 
 int g_tma_force_bn = 0;
+unsigned long long* g_tma_trace = nullptr;
+int g_tma_debug = 0;
 
 }  // namespace
 
-void gemm_tma_set_force_bn(int bn) { g_tma_force_bn = bn; }
+void gemm_tma_set_force_bn(int bn) { g_tma_force_bn = bn & 0xFFFF; g_tma_debug = bn >> 16; }
+void gemm_tma_set_trace(unsigned long long* buf) { g_tma_trace = buf; }
 
 int gemm_tma(const GemmParams& p, cudaStream_t stream) {
   if (p.M <= 0 || p.N <= 0) return GPS_OK;
@@ -476,6 +564,8 @@ int gemm_tma(const GemmParams& p, cudaStream_t stream) {
   splitk = (int)ceil_div(nkb, a.kb_per_split);
   a.p.splitk = p.splitk > 1 ? 2 : 1;   // "accumulate atomically" flag
   a.tmem_cols = a.BN <= 32 ? 32 : a.BN <= 64 ? 64 : a.BN <= 128 ? 128 : 256;
+  a.trace = g_tma_trace;
+  a.debug = g_tma_debug;
   const bool amn = p.ta != 0, bmn = p.tb != 0;
   // planes are addressed as stored: Aop[m,k] = A[m, k] (ta = 0: rows = M, cols = K) or A[k, m] (ta = 1: rows = K, cols = M)
   CUtensorMap tA, tB;

@@ -914,6 +914,13 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   cudaStream_t sa = (two_branches && sd) ? sd->s3 : st;   // stream of the attention-branch backward
   const int opt = opt_flags();
   const bool early_edge = (opt & 4) != 0;
+  // accumulators of the last two GEMMs of the pass are zeroed now, while their streams are idle, instead of on the tail
+  const bool gx_splitk = P.Wy >= 1024 && N > 0 && !((opt & 8) && P.gated && P.attn && sd && P.qkv_off > 0 && P.qkv_off < P.Wy);
+  if (P.Wy) {
+    if (sd) GPS_TRY(sd->order(st, s2));
+    GPS_CUDA(cudaMemsetAsync(P.gWcat, 0, (size_t)(P.Wy * d + P.Wy) * sizeof(float), s2));
+  }
+  if (gx_splitk) GPS_CUDA(cudaMemsetAsync(a->grad_x, 0, (size_t)(N * d) * sizeof(float), st));
   // [Ax|Bx|Dx|Ex] gradients are final long before [Q|K|V]'s: their share of dWcat and of g_x = gY1 Wcat is
   // computed under the attention backward, leaving only the [Q|K|V] share for the tail of the pass
   const bool split_tail = (opt & 8) && P.gated && P.attn && sd && P.qkv_off > 0 && P.qkv_off < P.Wy && N > 0;
@@ -1117,7 +1124,6 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     }
     if (split_tail) {
       const int64_t wl = P.qkv_off;
-      GPS_CUDA(cudaMemsetAsync(P.gWcat, 0, (size_t)(P.Wy * d + P.Wy) * sizeof(float), s2));
       GPS_TRY(wcat_wgrad(0, wl));
       GemmParams g;   // g_x = g_xloc + gY1[:, :wl] Wcat[:wl]
       g.M = (int)N; g.N = (int)d; g.K = (int)wl;
@@ -1197,7 +1203,6 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(gemm(g, st));
   } else if (P.Wy) {
     GPS_TRY(wfork(st));
-    GPS_CUDA(cudaMemsetAsync(P.gWcat, 0, (size_t)(P.Wy * d + P.Wy) * sizeof(float), s2));
     GemmParams w;
     w.M = (int)P.Wy; w.N = (int)d; w.K = (int)N;
     w.A = P.gY1; w.lda = (int)P.Wy; w.ta = 1; w.B = a->x; w.ldb = (int)d; w.tb = 1; w.C = P.gWcat; w.ldc = (int)d;
@@ -1218,10 +1223,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g.R1 = g_x_local; g.ldr1 = (int)d;
     g.R2 = P.attn ? P.g_hA : (P.perf ? P.g_xp : nullptr); g.ldr2 = (int)d;
     g.precision = prec;
-    if (P.Wy >= 1024 && N > 0) {   // long reduction, few output tiles: 2-way split-K fills the machine
-      GPS_CUDA(cudaMemsetAsync(a->grad_x, 0, (size_t)(N * d) * sizeof(float), st));
-      g.splitk = 4;
-    }
+    if (gx_splitk) g.splitk = 4;   // long reduction, few output tiles: split-K fills the machine (grad_x zeroed above)
     set_bpt(g, P.pt_cat, d, P.Wy);
     g.Ap = P.gY1_p; g.Bp = P.Wcat_p;
     GPS_TRY(gemm(g, st));
@@ -1304,6 +1306,11 @@ extern "C" int gps_gemm_planes(const void* A_hi, const void* A_lo, int64_t lda, 
   return rc;
 }
 extern "C" void gps_debug_set(int v) { gemm_tc_set_debug(v); }
+// bring-up hooks of the TMA GEMM: forced tile width (0 = heuristic) and a device buffer of 256 x 16 uint64 phase stamps
+extern "C" void gps_debug_tma(int force_bn, void* trace) {
+  gemm_tma_set_force_bn(force_bn);
+  gemm_tma_set_trace((unsigned long long*)trace);
+}
 
 extern "C" int gps_layer_plan(const GpsLayerArgs* args, GpsLayerPlan* plan) {
   GPS_REQUIRE(args && plan, GPS_ERR_ARG, "gps_layer_plan: null argument");

@@ -54,6 +54,9 @@ unsigned long long gps_launch_count(void);
 /* bring-up / tuning hook of the tcgen05 GEMM (tools/gemm_triage.py, tools/gemm_tune.py): low byte = stage
  * switches (1 no global loads, 2 no convert/store, 4 no MMA, 8 no epilogue), bits 8.. = forced tile width. 0 = normal. */
 void gps_debug_set(int v);
+/* bring-up hook of the TMA-fed GEMM (tools/gemm_trace.py): force_bn = forced tile width (0 = heuristic); trace = device
+ * buffer of 256 x 16 uint64 that the first 256 CTAs of each launch fill with globaltimer phase stamps (NULL = off) */
+void gps_debug_tma(int force_bn, void* trace);
 
 /* ------------------------------------------------------------------------------------------
  * Graph structure of one mini-batch (constant across the L layers and across fwd/bwd).
