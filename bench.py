@@ -216,14 +216,14 @@ def run_reference(args):
     spec, local, glob, heads, drop, adrop, batches = make_workload(args.workload, seed=0)
     layer, kind = cpu_reference_layer(spec, local, glob, heads, drop, adrop)
     cores = pick_cpu_threads(layer, batches, local)
-    steps = min(args.steps, 20)   # bounded sample: ~0.25 s per step at C3
-    times = time_cpu(layer, batches, steps, min(args.warmup, 3), local)
+    steps = min(args.steps, 20)   # bounded sample: ~0.05-0.25 s per step at C3 (each step is one full batch fwd+bwd)
+    times = time_cpu(layer, batches, steps, args.warmup, local)
     total = sum(times)
     B = spec.num_graphs
     value = B * len(times) / total
     out = {
         "impl": "reference", "metric": "graphs/sec GPSLayer fwd+bwd", "value": value, "unit": "graphs/s",
-        "n_gpus": args.gpus, "steps": len(times), "warmup": min(args.warmup, 3),
+        "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup,
         "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, spec, local, glob, heads, drop, adrop, 1),
@@ -278,14 +278,22 @@ def run_ours(args):
     cts = [(torch.randn(b.x.shape, generator=gen).to(dev), torch.randn(b.edge_attr.shape, generator=gen).to(dev))
            for b in cpu_batches]
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    grad_bucket = None
+    # Static gradient bucket (graphgps_b200.dp.GradBucket): every p.grad is a view of one flat buffer that the backward
+    # pass accumulates into, so CUDA-graph replays and the collective see the same memory.  For N > 1 the bucket is
+    # all-reduced in place (NCCL AVG): the early segment (FFN / out-proj / norms) on a communication stream as soon as
+    # the library signals it, under the rest of the backward pass; the late segment at the end.
+    from graphgps_b200.dp import GradBucket
+    bucket = GradBucket([layer])
+    if world > 1:
+        bucket.enable_overlap()
+        dist.all_reduce(torch.zeros(1, device=dev))      # communicator up before any capture
 
-    def allreduce_grads():
-        nonlocal grad_bucket
-        if world == 1:
-            return
-        from graphgps_b200.dp import allreduce_gradients
-        grad_bucket = allreduce_gradients(params, grad_bucket)
+    def allreduce_grads(overlap=True):
+        if world > 1:
+            if overlap:
+                bucket.allreduce_overlapped()
+            else:
+                bucket.allreduce()
 
     def step(i, bobj=None, reduce=True):
         b = bobj if bobj is not None else dev_batches[i % NUM_BATCHES]
@@ -295,8 +303,7 @@ def run_ours(args):
                                       num_graphs=b.num_graphs)
         if "_gps_b200_graph" in b.__dict__:
             bb.__dict__["_gps_b200_graph"] = b.__dict__["_gps_b200_graph"]
-        for p in params:
-            p.grad = None
+        bucket.zero_()
         x_in = bb.x
         out = layer(bb)
         if gated:
@@ -319,29 +326,51 @@ def run_ours(args):
         step(i)
     barrier()
     graphs = None
+    graphs_local = None            # the same step without the collectives (N > 1: exposes the all-reduce cost)
     launches_per_step = None
+    collective_in_graph = False
+
+    def capture_all(reduce):
+        out = []
+        nonlocal launches_per_step
+        for i in range(NUM_BATCHES):
+            g = torch.cuda.CUDAGraph()
+            l0 = lib.gps_launch_count()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                step(i, reduce=reduce)
+            launches_per_step = lib.gps_launch_count() - l0
+            out.append(g)
+        return out
+
     if args.graph:
-        graphs = []
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for i in range(NUM_BATCHES):
-                step(i, reduce=False)
+                step(i, reduce=True)
         torch.cuda.current_stream().wait_stream(side)
-        for i in range(NUM_BATCHES):
-            g = torch.cuda.CUDAGraph()
-            l0 = lib.gps_launch_count()
-            with torch.cuda.graph(g):
-                step(i, reduce=False)
-            launches_per_step = lib.gps_launch_count() - l0
-            graphs.append(g)
+        barrier()
+        if world > 1:
+            try:     # NCCL collectives captured in the same graph as the step
+                graphs = capture_all(True)
+                collective_in_graph = True
+            except Exception as e:   # noqa: BLE001
+                sys.stderr.write(f"[bench] capturing the collectives failed ({e!r}); they run after each replay\n")
+                graphs = None
+                torch.cuda.synchronize()
+            graphs_local = capture_all(False)
+            if graphs is None:
+                graphs = graphs_local
+        else:
+            graphs = capture_all(False)
 
     def run_step(i):
         if graphs is None:
             step(i)
         else:
             graphs[i % NUM_BATCHES].replay()
-            allreduce_grads()
+            if world > 1 and not collective_in_graph:
+                allreduce_grads()
 
     for i in range(args.warmup):
         run_step(i)
@@ -368,6 +397,25 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
+
+    # N > 1: the same replays without the collectives -> what the all-reduce still costs after overlap
+    local_ms = None
+    if world > 1 and graphs_local is not None:
+        for i in range(args.warmup):
+            graphs_local[i % NUM_BATCHES].replay()
+        barrier()
+        le = []
+        for i in range(args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            graphs_local[i % NUM_BATCHES].replay()
+            e1.record()
+            le.append((e0, e1))
+        barrier()
+        tl = torch.tensor([sum(a.elapsed_time(b) for a, b in le)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        local_ms = float(tl.item()) / args.steps
 
     # eager (no CUDA graph) number for the same loop, reported alongside
     eager_ms = None
@@ -404,8 +452,7 @@ def run_ours(args):
         bb = graphgps_b200.GraphBatch(x=sb.x.detach().requires_grad_(True), edge_index=sb.edge_index,
                                       edge_attr=sb.edge_attr.detach().requires_grad_(True), batch=sb.batch,
                                       num_graphs=sb.num_graphs)     # no cached structure: gps_graph_build runs
-        for p in params:
-            p.grad = None
+        bucket.zero_()
         x_in = bb.x
         out = layer(bb)
         ctx, cte = cts[i]
@@ -423,7 +470,7 @@ def run_ours(args):
         e2e_graphs = []
         for i in range(NUM_BATCHES):
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
                 outs[i] = e2e_body(i)
             e2e_graphs.append(g)
     s_h2d, s_d2h, s_cmp = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.current_stream()
@@ -455,7 +502,7 @@ def run_ours(args):
                 e2e_graphs[i].replay()
             else:
                 outs[i] = e2e_body(i)
-            allreduce_grads()
+            allreduce_grads(overlap=False)   # the early-gradient event lives inside the captured graph here
             ev_cmp[k].record(s_cmp)
             with torch.cuda.stream(s_d2h):
                 s_d2h.wait_event(ev_cmp[k])
@@ -482,63 +529,50 @@ def run_ours(args):
     # ONE captured CUDA graph over a resident batch (graph structure shared by all layers).  Measured last and
     # guarded, so a failure here can only drop this extra key.
     stack = None
-    if world == 1 and args.graph and spec.layers > 1:
+    if args.graph and spec.layers > 1:
         try:
             torch.manual_seed(1)
-            layers = [layer] + [graphgps_b200.GPSLayer(spec.dim, local, glob, heads, dropout=drop, attn_dropout=adrop,
-                                                       precision=args.precision).to(dev).train()
-                                for _ in range(spec.layers - 1)]
-            sparams = [p for l in layers for p in l.parameters()]
-
-            def stack_step(i):
-                b = dev_batches[i]
-                bb = graphgps_b200.GraphBatch(x=b.x.detach().requires_grad_(True), edge_index=b.edge_index,
-                                              edge_attr=b.edge_attr.detach().requires_grad_(True), batch=b.batch,
-                                              num_graphs=b.num_graphs)
-                bb.__dict__["_gps_b200_graph"] = b.__dict__["_gps_b200_graph"]
-                for p in sparams:
-                    p.grad = None
-                out = bb
-                for l in layers:
-                    out = l(out)
-                if gated:
-                    torch.autograd.backward([out.x, out.edge_attr], [cts[i][0], cts[i][1]])
-                else:
-                    torch.autograd.backward([out.x], [cts[i][0]])
-
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for i in range(2):
-                    stack_step(i)
-                    stack_step(i)
-            torch.cuda.current_stream().wait_stream(side)
-            sgraphs = []
+            gstack = graphgps_b200.GPSStack(spec.layers, spec.dim, local, glob, heads, dropout=drop, attn_dropout=adrop,
+                                            precision=args.precision).to(dev).train()
+            sbucket = gstack.make_grad_bucket(overlap=world > 1)
+            coll = (lambda: sbucket.allreduce_overlapped()) if world > 1 else None
+            steps_c = []
             for i in range(2):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    stack_step(i)
-                sgraphs.append(g)
+                b = dev_batches[i]
+                try:
+                    steps_c.append(gstack.capture(b, cts[i][0], cts[i][1] if gated else None, bucket=sbucket,
+                                                  collective=coll))
+                except Exception:   # noqa: BLE001 - collectives not capturable here: stack without them, said so below
+                    if coll is None:
+                        raise
+                    coll = None
+                    torch.cuda.synchronize()
+                    steps_c.append(gstack.capture(b, cts[i][0], cts[i][1] if gated else None, bucket=sbucket))
             for i in range(4):
-                sgraphs[i % 2].replay()
-            torch.cuda.synchronize()
+                steps_c[i % 2].replay()
+            barrier()
             se = []
-            nst = min(args.steps, 20)
+            nst = min(args.steps, 50)
             for i in range(nst):
                 flush.zero_()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                sgraphs[i % 2].replay()
+                steps_c[i % 2].replay()
                 e1.record()
                 se.append((e0, e1))
-            torch.cuda.synchronize()
-            sms = sum(a.elapsed_time(b) for a, b in se) / nst
-            stack = {"layers": spec.layers, "measured": True, "ms_per_step": sms,
-                     "graphs_per_s": spec.num_graphs / (sms * 1e-3),
-                     "how": f"{spec.layers} GPSLayers fwd+bwd in one captured CUDA graph, batch resident, L2 flushed "
-                            f"between steps, {nst} steps"}
+            barrier()
+            ts = torch.tensor([sum(a.elapsed_time(b) for a, b in se)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+            sms = float(ts.item()) / nst
+            stack = {"layers": spec.layers, "measured": True, "ms_per_step": sms, "ms_per_layer": sms / spec.layers,
+                     "graphs_per_s": spec.num_graphs * world / (sms * 1e-3),
+                     "how": f"graphgps_b200.GPSStack: {spec.layers} GPSLayers fwd+bwd in one captured CUDA graph per rank "
+                            f"(shared graph structure, plane hand-off between layers, one gradient bucket"
+                            + (", per-layer all-reduce overlapped with the backward of the layers below" if coll else "")
+                            + f"), batch resident, L2 flushed between steps, {nst} steps, max over ranks"}
         except Exception as e:   # noqa: BLE001 - the headline numbers above must survive
-            stack = {"layers": spec.layers, "measured": False, "error": repr(e)[:200]}
+            stack = {"layers": spec.layers, "measured": False, "error": repr(e)[:300]}
 
     if rank == 0:
         B = spec.num_graphs
@@ -559,8 +593,16 @@ def run_ours(args):
                     "how": "pinned host -> H2D -> graph build + fwd + bwd -> D2H(x_out, grad_x); copies on their own "
                            "streams, 2 steps deep; first H2D to last D2H by device events"},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
-            "execution": ("CUDA graph replay (one captured fwd+bwd graph per rotating batch shape)" if args.graph
-                          else "eager launches"),
+            "gemm_fallbacks": int(lib.gps_fallback_count()),
+            "allreduce": (None if world == 1 else {
+                "bytes": int(bucket.flat.numel() * 4), "in_graph": bool(collective_in_graph),
+                "how": "in-place NCCL AVG on the static gradient bucket; early segment (FFN/out-proj/norm gradients) on a "
+                       "communication stream under the rest of the backward pass, late segment at the end",
+                "ms_per_step_without_collectives": local_ms,
+                "exposed_ms_per_step": (None if local_ms is None else ms_total / args.steps - local_ms)}),
+            "execution": ("CUDA graph replay (one captured fwd+bwd"
+                          + ("+all-reduce" if collective_in_graph else "") + " graph per rotating batch shape)"
+                          if args.graph else "eager launches"),
             "eager": ({"ms_per_step": eager_ms, "value": B * world / (eager_ms * 1e-3)} if eager_ms else None),
             "clocks": clocks, "roofline": roof,
             "cpu_baseline": {"value": cpu_value, "unit": "graphs/s", "cores": cores, "kind": kind,
@@ -589,10 +631,11 @@ def roofline_probe(lib, layer, b, spec, heads, args):
     N, E, d = gs.N, gs.E, spec.dim
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    # DRAM bytes per launch from the committed `ncu --set full` capture of THIS workload (null when none was taken)
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r1_roofline_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r2_roofline_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath))
+        traffic = json.load(open(tpath)).get(f"{args.workload}:{args.precision}", {})
     res = {}
 
     def timeit(fn, reps=10):
@@ -615,13 +658,25 @@ def roofline_probe(lib, layer, b, spec, heads, args):
     W = torch.randn(Wy, d, device=dev) / d ** 0.5
     gY = torch.randn(N, Wy, device=dev)
     gx = torch.zeros(N, d, device=dev)
+
+    def planes(t):   # bf16 hi/lo operand planes, as the producing kernels of the layer write them
+        r, c = t.shape
+        ld = (c + 7) // 8 * 8
+        buf = torch.zeros(2, r, ld, dtype=torch.bfloat16, device=dev)
+        _ = lib.gps_to_planes(t.data_ptr(), t.stride(0), r, c, buf[0].data_ptr(), buf[1].data_ptr() if prec == 0 else 0, ld, stream)
+        return buf, ld
+
+    gYp, ldg = planes(gY)
+    Wp, ldw = planes(W)
     # split-K 4 accumulates atomically into gx (the layer zeroes it with a memset that is not part of the kernel)
-    t_g = timeit(lambda: lib.gps_gemm(gY.data_ptr(), Wy, 0, W.data_ptr(), d, 1, gx.data_ptr(), d, N, d, Wy, 4, prec, 0,
-                                      stream))
+    t_g = timeit(lambda: lib.gps_gemm_planes(gYp[0].data_ptr(), gYp[1].data_ptr() if prec == 0 else 0, ldg, 0,
+                                             Wp[0].data_ptr(), Wp[1].data_ptr() if prec == 0 else 0, ldw, 1,
+                                             gx.data_ptr(), d, 0, 0, 0, N, d, Wy, 4, prec, 0, stream))
     flops = 2.0 * N * Wy * d
     res["gemm"] = {"bound": "tensor", "achieved": flops / t_g / 1e12, "peak": pk["tensor"], "unit": "TFLOP/s",
                    "frac": flops / t_g / 1e12 / pk["tensor"], "traffic": traffic.get("gemm_dgrad_x"), "seconds": t_g,
-                   "kernel": "k_gemm_tc data gradient g_x[N,d] = gY1[N,7d] x Wcat[7d,d] (tcgen05, split-bf16 x3, split-K 4)",
+                   "kernel": "k_gemm_tma data gradient g_x[N,d] = gY1[N,7d] x Wcat[7d,d] (TMA-fed tcgen05 on bf16 hi/lo planes, "
+                             + ("3 MMAs per product" if prec == 0 else "1 MMA per product") + ", split-K 4)",
                    "algorithmic_flops": flops, "peak_source": pk["source"]}
     Y = torch.randn(N, Wy, device=dev)
     Ce = torch.randn(E, d, device=dev)
@@ -646,7 +701,7 @@ def roofline_probe(lib, layer, b, spec, heads, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="pcqm4m-small", choices=sorted(WORKLOADS))

@@ -37,6 +37,10 @@ class GpsLinear(C.Structure):
     _fields_ = [("weight", _fp), ("bias", _fp), ("grad_weight", _fp), ("grad_bias", _fp)]
 
 
+class GpsPlanes(C.Structure):
+    _fields_ = [("hi", _fp), ("lo", _fp), ("ld", C.c_int64)]
+
+
 class GpsLayerArgs(C.Structure):
     _fields_ = [
         ("d", C.c_int64), ("heads", C.c_int64),
@@ -61,13 +65,16 @@ class GpsLayerArgs(C.Structure):
         ("workspace", _fp), ("workspace_bytes", C.c_int64),
         ("offset_dev", _fp),
         ("gcn_conv", GpsLinear),
+        ("ev_grads_early", _fp),
+        ("x_planes_in", GpsPlanes), ("e_planes_in", GpsPlanes), ("x_planes_out", GpsPlanes), ("e_planes_out", GpsPlanes),
+        ("wplanes", _fp), ("wplanes_bytes", C.c_int64), ("wplanes_valid", C.c_int32), ("reserved2", C.c_int32),
     ]
 
 
 class GpsLayerPlan(C.Structure):
     _fields_ = [("saved_bytes", C.c_int64), ("fwd_workspace_bytes", C.c_int64),
                 ("bwd_workspace_bytes", C.c_int64), ("fwd_launches", C.c_int64),
-                ("bwd_launches", C.c_int64)]
+                ("bwd_launches", C.c_int64), ("wplanes_bytes", C.c_int64)]
 
 
 # every symbol include/gps_b200.h declares: name -> (restype, argtypes)

@@ -212,6 +212,7 @@ struct Plan {
   Planes x_p, e_p, O_p, s_p, hid_p, agg_p, h1_p, Wcat_p, C_p, out_p, ff1_p, ff2_p, g0_p, g1_p, pq_p, pk_p, pv_p;
   Planes gt_p, ghid_p, ghA_p, ge_p, gY1_p, gtmp_p, gtmp2_p, gtmp3_p, gl1_p, gh1_p;
   int64_t saved_bytes;
+  int64_t wplanes_bytes;
   // forward workspace
   double* fstats;
   int64_t fwd_bytes;
@@ -329,27 +330,52 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
   };
   if (P->use_planes) {
     const int64_t kout = P->perf ? P->inner : d;
-    P->x_p = mkplanes(S, N, d);
-    if (P->gated || P->gine) P->e_p = mkplanes(S, E, d);
+    auto handed = [&](const GpsPlanes& g) {   // planes written by the previous layer of the stack
+      Planes q;
+      q.hi = (__nv_bfloat16*)g.hi; q.lo = lo ? (__nv_bfloat16*)g.lo : nullptr; q.ld = g.ld;
+      return q;
+    };
+    const bool x_in = a->x_planes_in.hi && (!lo || a->x_planes_in.lo) && a->x_planes_in.ld >= d && a->x_planes_in.ld % 8 == 0;
+    const bool e_in = a->e_planes_in.hi && (!lo || a->e_planes_in.lo) && a->e_planes_in.ld >= d && a->e_planes_in.ld % 8 == 0;
+    P->x_p = x_in ? handed(a->x_planes_in) : mkplanes(S, N, d);
+    if (P->gated || P->gine) P->e_p = e_in ? handed(a->e_planes_in) : mkplanes(S, E, d);
     if (P->attn || P->perf) P->O_p = mkplanes(S, N, kout);
     P->s_p = mkplanes(S, N, d);
     P->hid_p = mkplanes(S, N, 2 * d);
     if (P->gine) {
       P->agg_p = mkplanes(S, N, d);
       P->h1_p = mkplanes(S, N, d);
-      P->g0_p = mkplanes(S, d, d);
-      P->g1_p = mkplanes(S, d, d);
     }
-    if (P->Wy) P->Wcat_p = mkplanes(S, P->Wy, d);
-    if (P->gated) P->C_p = mkplanes(S, d, d);
-    if (P->attn || P->perf) P->out_p = mkplanes(S, d, kout);
-    P->ff1_p = mkplanes(S, 2 * d, d);
-    P->ff2_p = mkplanes(S, d, 2 * d);
-    if (P->perf) {
-      P->pq_p = mkplanes(S, P->inner, d);
-      P->pk_p = mkplanes(S, P->inner, d);
-      P->pv_p = mkplanes(S, P->inner, d);
+    // weight planes: in the caller's persistent buffer when one is given (packed once per optimiser step), else in `saved`
+    Arena Wa(bind ? a->wplanes : nullptr, a->wplanes_bytes);
+    const bool persistent = bind && a->wplanes != nullptr;
+    Arena& WA = persistent ? Wa : S;
+    Arena Wc(nullptr, 0);            // size of the persistent buffer, counted independently of `saved`
+    for (int pass = 0; pass < 2; ++pass) {
+      Arena& A = pass == 0 ? Wc : WA;
+      Planes wcat, cp, outp, f1, f2, g0, g1, pq, pk, pv;
+      if (P->Wy) wcat = mkplanes(A, P->Wy, d);
+      if (P->gated) cp = mkplanes(A, d, d);
+      if (P->attn || P->perf) outp = mkplanes(A, d, kout);
+      f1 = mkplanes(A, 2 * d, d);
+      f2 = mkplanes(A, d, 2 * d);
+      if (P->gine) {
+        g0 = mkplanes(A, d, d);
+        g1 = mkplanes(A, d, d);
+      }
+      if (P->perf) {
+        pq = mkplanes(A, P->inner, d);
+        pk = mkplanes(A, P->inner, d);
+        pv = mkplanes(A, P->inner, d);
+      }
+      if (pass == 1) {
+        P->Wcat_p = wcat; P->C_p = cp; P->out_p = outp; P->ff1_p = f1; P->ff2_p = f2; P->g0_p = g0; P->g1_p = g1;
+        P->pq_p = pq; P->pk_p = pk; P->pv_p = pv;
+      }
     }
+    P->wplanes_bytes = Wc.used;
+    GPS_REQUIRE(!Wa.overflow, GPS_ERR_ARG, "wplanes buffer too small (%lld < %lld)", (long long)a->wplanes_bytes,
+                (long long)Wc.used);
   }
   if (P->prepack && !P->use_planes) {
     const int64_t kout = P->perf ? P->inner : d;
@@ -615,6 +641,16 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     return c;
   };
   auto stats = [&](int which) -> double* { return train ? P.fstats + (int64_t)which * 2 * d : nullptr; };
+  auto out_planes = [&](const GpsPlanes& g) {   // planes of this layer's outputs for the next layer of the stack
+    Planes q;
+    if (P.use_planes && g.hi && g.ld >= d && g.ld % 8 == 0) {
+      q.hi = (__nv_bfloat16*)g.hi;
+      q.lo = a->precision == GPS_PREC_FP32 ? (__nv_bfloat16*)g.lo : nullptr;
+      q.ld = g.ld;
+      if (a->precision == GPS_PREC_FP32 && !q.lo) q = Planes();
+    }
+    return q;
+  };
 
   if (train) GPS_CUDA(cudaMemsetAsync(P.fstats, 0, (size_t)BN_COUNT * 2 * d * sizeof(double), st));
   Side* sd = side_stream();
@@ -647,8 +683,10 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
       if (src && dst.hi && rows > 0) it[ni++] = ToPlanesItem{src, ld, (int)rows, (int)cols, dst};
     };
     const int64_t kout = P.perf ? P.inner : d;
-    add(a->x, d, N, d, P.x_p);
-    if (P.gated || P.gine) add(a->edge_attr, d, E, d, P.e_p);
+    if (P.x_p.hi != (__nv_bfloat16*)a->x_planes_in.hi) add(a->x, d, N, d, P.x_p);
+    if ((P.gated || P.gine) && P.e_p.hi != (__nv_bfloat16*)a->e_planes_in.hi) add(a->edge_attr, d, E, d, P.e_p);
+    const bool wvalid = a->wplanes && a->wplanes_valid;
+    if (wvalid) goto weights_done;
     if (P.gated) {
       add(a->gcn_A.weight, d, d, d, P.Wcat_p.rows(0));
       add(a->gcn_B.weight, d, d, d, P.Wcat_p.rows(d));
@@ -670,6 +708,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
       add(a->perf_k.weight, d, P.inner, d, P.pk_p);
       add(a->perf_v.weight, d, P.inner, d, P.pv_p);
     }
+  weights_done:
     GPS_TRY(to_planes(it, ni, st));
   }
   if (P.prepack && !P.use_planes) {
@@ -755,7 +794,7 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(bn_act_residual(P.xt, d, a->x, P.xloc, N, d, bn_view_fwd(P, a, BN_X, a->bn_node_x, N), act, drop(GPS_SITE_GCN_X),
                             stats(BN_L), st));
     GPS_TRY(bn_act_residual(P.ehat, d, a->edge_attr, a->edge_out, E, d, bn_view_fwd(P, a, BN_E, a->bn_edge_e, E), act,
-                            drop(GPS_SITE_GCN_E), nullptr, st));
+                            drop(GPS_SITE_GCN_E), nullptr, st, out_planes(a->e_planes_out)));
   } else if (P.gine) {
     GPS_TRY(gine_fwd(a->graph, d, a->x, a->edge_attr, a->gine_eps, P.agg, st, P.agg_p));
     GemmParams g;  // h1 = act(agg W0^T + b0)
@@ -872,7 +911,8 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     set_bpk(g2, P.pk_ff2, d, 2 * d, 0);
     g2.Ap = P.hid_p; g2.Bp = P.ff2_p;
     GPS_TRY(gemm(g2, st));
-    GPS_TRY(bn_combine(P.t, bn_view_fwd(P, a, BN_2, a->norm2, N), nullptr, BnView(), a->x_out, N, d, st));  // :229
+    GPS_TRY(bn_combine(P.t, bn_view_fwd(P, a, BN_2, a->norm2, N), nullptr, BnView(), a->x_out, N, d, st,
+                       out_planes(a->x_planes_out)));  // :229
   }
   return GPS_OK;
 }
@@ -914,6 +954,12 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   cudaStream_t sa = (two_branches && sd) ? sd->s3 : st;   // stream of the attention-branch backward
   const int opt = opt_flags();
   const bool early_edge = (opt & 4) != 0;
+  // data-parallel hook: the caller's event is recorded on the weight-gradient stream once the early gradient group
+  // (FFN, attention output projection, norm2 / norm1_local / norm1_attn) has been enqueued there
+  auto early_done = [&]() -> int {
+    if (a->ev_grads_early) GPS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_grads_early, s2));
+    return GPS_OK;
+  };
   // accumulators of the last two GEMMs of the pass are zeroed now, while their streams are idle, instead of on the tail
   const bool gx_splitk = P.Wy >= 1024 && N > 0 && !((opt & 8) && P.gated && P.attn && sd && P.qkv_off > 0 && P.qkv_off < P.Wy);
   if (P.Wy) {
@@ -1014,6 +1060,10 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(bn_bwd_apply(P.g_s, d, P.xloc, d, N, d, v, -1, nodrop, sums(BN_L), P.g_xloc, d,
                          a->norm1_local.grad_weight, a->norm1_local.grad_bias, st, g_grads_accumulate, P.gl1_p));
   }
+  if (!P.attn && !P.perf) {   // no global model: the early group ends with norm1_local's gradients (stream st)
+    GPS_TRY(wfork(st));
+    GPS_TRY(early_done());
+  }
   if (two_branches && sd) GPS_TRY(sd->order(st, sa));   // attention-branch backward runs next to the local-model backward
   if (P.attn) {
     BnView v = bn_view(P, BN_A, a->norm1_attn);
@@ -1037,6 +1087,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(gemm(g, sa));
     GPS_TRY(wfork(sa));
     GPS_TRY(linear_wgrad(g_ao, d, P.O, d, N, d, d, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, s2, g_ao_p, P.O_p));
+    GPS_TRY(early_done());
     const float* Q = P.Y1 + P.qkv_off;
     float* gQ = P.gY1 + P.qkv_off;
     GPS_TRY(attention_bwd(a->graph, P.H, P.hd, Q, Q + d, Q + 2 * d, P.Wy, P.O, P.g_O, d, P.lse, P.delta, gQ, gQ + d,
@@ -1063,6 +1114,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(gemm(g, sa));
     GPS_TRY(wfork(sa));
     GPS_TRY(linear_wgrad(g_ao, d, P.O, inner, N, d, inner, a->attn_out.grad_weight, a->attn_out.grad_bias, prec, s2));
+    GPS_TRY(early_done());
     // linear attention and feature maps (performer_layer.py:200-205, 119-144)
     if (P.perf_pairwise)
       GPS_TRY(perf_quad_bwd(a->graph, P.H, P.m, P.pnmax, P.pfq, P.pfk, P.pV, P.pgmax, P.O, P.pden, P.g_O, P.g_pden,
@@ -1321,6 +1373,7 @@ extern "C" int gps_layer_plan(const GpsLayerArgs* args, GpsLayerPlan* plan) {
   plan->bwd_workspace_bytes = P.bwd_bytes;
   plan->fwd_launches = 0;
   plan->bwd_launches = 0;
+  plan->wplanes_bytes = P.wplanes_bytes;
   return GPS_OK;
 }
 

@@ -14,7 +14,7 @@ no copy-in / scale / copy-out) and can be captured in the same CUDA graph as the
 laid out in two contiguous groups per layer - "early" (FFN, attention output projection and the three
 GPSLayer norms, final a few hundred microseconds before the backward pass ends) and "late" (the node/edge
 projections, final only at the very end) - so the early group's collective can be issued on a side stream
-while the rest of the backward pass still runs (`GradBucket.allreduce(overlap=...)`).
+while the rest of the backward pass still runs (`GradBucket.enable_overlap()` / `allreduce_overlapped()`).
 """
 from __future__ import annotations
 
@@ -75,6 +75,35 @@ class GradBucket:
     def zero_(self):
         self.flat.zero_()
         return self
+
+    def enable_overlap(self):
+        """Give every layer an event that gps_layer_backward records when its early gradient group is final, and a
+        communication stream on which `allreduce_overlapped` runs the collectives."""
+        dev = self.flat.device
+        self.comm_stream = torch.cuda.Stream(device=dev)
+        self.events = []
+        for layer in self.layers:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))     # materialise the cudaEvent_t handle
+            layer.__dict__["grad_early_event"] = ev
+            self.events.append(ev)
+        return self
+
+    def allreduce_overlapped(self, group=None):
+        """Call right after backward() has been enqueued (layers ran last-to-first).  Per layer, the early segment is
+        reduced as soon as its event fires - under the rest of that layer's backward pass and under the backward of the
+        layers below it - and the late segment when the whole pass is done; the caller's stream waits for both.
+        Capturable into the same CUDA graph as the step."""
+        cur = torch.cuda.current_stream(self.flat.device)
+        cs = self.comm_stream
+        with torch.cuda.stream(cs):
+            for li in reversed(range(len(self.layers))):
+                cs.wait_event(self.events[li])
+                self.allreduce(group, segments=[self.segment(li, True)])
+            cs.wait_stream(cur)
+            late = [self.segment(li, False) for li in reversed(range(len(self.layers)))]
+            self.allreduce(group, segments=[t for t in late if t is not None])
+        cur.wait_stream(cs)
 
     def segment(self, layer: int, early: bool):
         for li, e, b, en in self.segments:

@@ -58,6 +58,30 @@ def _workspace(device, nbytes):
     return held[-1]
 
 
+_PLANES_ATTR = "_gps_b200_planes"
+
+
+def _batch_planes_get(batch):
+    try:
+        v = getattr(batch, _PLANES_ATTR, None)
+    except Exception:
+        v = None
+    return v if isinstance(v, dict) else None
+
+
+def _batch_planes_put(batch, produced, lo):
+    """Remember, on the batch object, the operand planes this layer wrote next to its outputs, keyed by the identity
+    (address, version, shape) of the tensors they mirror: the next GPSLayer uses them only if batch.x / batch.edge_attr
+    are still exactly those tensors."""
+    rec = {}
+    for name, (t, buf) in (produced or {}).items():
+        rec[name] = ((t.data_ptr(), t._version, tuple(t.shape), lo), buf)
+    try:
+        setattr(batch, _PLANES_ATTR, rec)
+    except Exception:
+        pass
+
+
 class _GatedGCNParams(nn.Module):
     """Parameter container with the names of graphgps/layer/gatedgcn_layer.py:21-38."""
 
@@ -158,6 +182,7 @@ class _GPSLayerFn(torch.autograd.Function):
         args.x_out, args.edge_out = x_out.data_ptr(), _lib.ptr(e_out)
         args.saved, args.saved_bytes = saved.data_ptr(), saved.numel()
         args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
+        hand = layer._handoff_args(args, plan, params, x, e, x_out, e_out)
         snap = None
         if layer.training and (layer.dropout > 0 or layer.attn_dropout > 0):
             snap = _next_dropout_offset(dev)
@@ -165,6 +190,7 @@ class _GPSLayerFn(torch.autograd.Function):
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.gps_layer_forward(C.byref(args), stream), "gps_layer_forward")
         ctx.layer, ctx.gs, ctx.saved_buf, ctx.snap = layer, gs, saved, snap
+        ctx.hand = hand
         ctx.seed, ctx.offset, ctx.training = args.seed, args.offset, bool(args.training)
         ctx.save_for_backward(x, e, *params)
         if e_out is not None:
@@ -210,6 +236,12 @@ class _GPSLayerFn(torch.autograd.Function):
         args.grad_x, args.grad_edge_attr = g_x.data_ptr(), _lib.ptr(g_e)
         args.saved, args.saved_bytes = ctx.saved_buf.data_ptr(), ctx.saved_buf.numel()
         args.workspace, args.workspace_bytes = ws.data_ptr(), ws.numel()
+        if ctx.hand is not None:
+            args.x_planes_in, args.e_planes_in, args.wplanes, args.wplanes_bytes = ctx.hand[:4]
+            args.wplanes_valid = 1
+        ev = layer.__dict__.get("grad_early_event")
+        if ev is not None:
+            args.ev_grads_early = ev.cuda_event
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.gps_layer_backward(C.byref(args), stream), "gps_layer_backward")
         # (ctx.saved_buf stays alive with the autograd node: backward(retain_graph=True) may run again)
@@ -308,6 +340,56 @@ class GPSLayer(nn.Module):
         self._grad_numel = sum(self._grad_sizes)
         self._plan_cache = {}
 
+    # ------------------------------------------------------------------ operand planes across layers / steps
+    def _handoff_args(self, args, plan, params, x, e, x_out, e_out):
+        """Fills the ABI-3 plane fields: (i) the bf16 hi/lo planes of x / edge_attr that the previous GPSLayer of the
+        model wrote next to its outputs (gps_model.py:100,105-108 chains the layers on one batch object), so this layer
+        skips converting its inputs; (ii) plane buffers for this layer's own outputs; (iii) the persistent weight-plane
+        buffer, re-packed only when a parameter changed (once per optimiser step, not once per forward call).
+        Returns what backward needs to see again, and keeps the buffers alive through the autograd node."""
+        if plan[2] <= 0 or not self.__dict__.get("plane_handoff", True):
+            return None
+        dev = x.device
+        lo = self.precision == "fp32"
+
+        def planes_of(t):
+            buf = torch.empty((2 if lo else 1, t.shape[0], (t.shape[1] + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)
+            return buf, _lib.GpsPlanes(buf[0].data_ptr(), buf[1].data_ptr() if lo else 0, buf.shape[2])
+
+        keep = []
+        zero = _lib.GpsPlanes(0, 0, 0)
+        xin, ein = zero, zero
+        src = self.__dict__.pop("_planes_in", None) or {}
+        for name, t in (("x", x), ("e", e)):
+            h = src.get(name)
+            if h is not None and h[0] == (t.data_ptr(), t._version, tuple(t.shape), lo):
+                keep.append(h[1])
+                pl = _lib.GpsPlanes(h[1][0].data_ptr(), h[1][1].data_ptr() if lo else 0, h[1].shape[2])
+                if name == "x":
+                    xin = pl
+                else:
+                    ein = pl
+        args.x_planes_in, args.e_planes_in = xin, ein
+        out = {}
+        xb, args.x_planes_out = planes_of(x_out)
+        out["x"] = (x_out, xb)
+        if e_out is not None:
+            eb, args.e_planes_out = planes_of(e_out)
+            out["e"] = (e_out, eb)
+        self.__dict__["_planes_out"] = out
+        # persistent weight planes
+        key = (tuple((p.data_ptr(), p._version) for p in params), self.precision, plan[2])
+        wp = self.__dict__.get("_wplanes")
+        if wp is None or wp[0].numel() < plan[2] or wp[0].device != dev:
+            wp = [torch.empty(plan[2] + 256, dtype=torch.uint8, device=dev), None]
+            self.__dict__["_wplanes"] = wp
+        args.wplanes, args.wplanes_bytes = wp[0].data_ptr(), wp[0].numel()
+        capturing = torch.cuda.is_current_stream_capturing()
+        args.wplanes_valid = 1 if (wp[1] == key and not capturing) else 0   # a captured graph always re-packs
+        wp[1] = key
+        keep.append(wp[0])
+        return (xin, ein, args.wplanes, args.wplanes_bytes, keep)
+
     def _bucket_grads(self, named):
         """{name: .grad view} when every parameter's .grad is a view of this layer's static bucket, else None."""
         b = self.__dict__.get("_grad_bucket")
@@ -329,7 +411,8 @@ class GPSLayer(nn.Module):
         if hit is None:
             plan = _lib.GpsLayerPlan()
             _lib.check(_lib.load().gps_layer_plan(C.byref(args), C.byref(plan)), "gps_layer_plan")
-            hit = (int(plan.saved_bytes), int(max(plan.fwd_workspace_bytes, plan.bwd_workspace_bytes)))
+            hit = (int(plan.saved_bytes), int(max(plan.fwd_workspace_bytes, plan.bwd_workspace_bytes)),
+                   int(plan.wplanes_bytes))
             if len(self._plan_cache) > 64:
                 self._plan_cache.clear()
             self._plan_cache[key] = hit
@@ -444,11 +527,14 @@ class GPSLayer(nn.Module):
         gs = graph_of(batch)
         params = [p for _, p in self.named_parameters()]
         e_arg = e if e is not None else x.new_empty(0)
+        self.__dict__["_planes_in"] = _batch_planes_get(batch)
         out = _GPSLayerFn.apply(self, gs, x, e_arg, *params)
+        produced = self.__dict__.pop("_planes_out", None)
         if self.local_gnn_type == "CustomGatedGCN":
             batch.x, batch.edge_attr = out           # gps_layer.py:173-174, :231
         else:
             batch.x = out
+        _batch_planes_put(batch, produced, self.precision == "fp32")
         return batch
 
     def extra_repr(self):

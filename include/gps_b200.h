@@ -106,6 +106,14 @@ typedef struct {
   float* grad_bias;
 } GpsLinear;
 
+/* bf16 hi/lo planes of an fp32 [rows, cols] tensor: row-major, pitch ld elements (multiple of 8); lo may be NULL in
+ * GPS_PREC_BF16 mode */
+typedef struct {
+  void* hi;
+  void* lo;
+  int64_t ld;
+} GpsPlanes;
+
 /* ------------------------------------------------------------------------------------------
  * GPSLayer forward / backward  (gps_layer.py:155-257; GatedGCN gatedgcn_layer.py:45-136)
  * state_dict names in comments are the reference's.
@@ -165,6 +173,23 @@ typedef struct {
   /* ABI 2: PyG GCNConv(dim_h, dim_h) local model (gps_layer.py:49-51): weight = local_model.lin.weight [d,d]
    * (its Linear has no bias), bias = local_model.bias [d], added after the normalised aggregation. */
   GpsLinear gcn_conv;
+
+  /* ABI 3 (backward, optional): a cudaEvent_t the library records as soon as the "early" parameter gradients are
+   * final - ff_linear1/2, the attention output projection, norm2, norm1_local, norm1_attn - a few hundred microseconds
+   * before the pass ends.  A data-parallel caller makes its communication stream wait on it and all-reduces that
+   * part of the gradient bucket under the rest of the backward pass (graphgps_b200/dp.py).  NULL = not recorded. */
+  void* ev_grads_early;
+
+  /* ABI 3 (optional): operand-plane hand-off between consecutive layers of a GPSModel (network/gps_model.py:100,105-108)
+   * and persistent weight planes.  A plane pair is the bf16 hi/lo image of an fp32 tensor (see gps_to_planes).
+   *  x_planes_in / e_planes_in   planes of x / edge_attr written by the previous layer: the layer skips its own
+   *                              conversion of the inputs (hi == NULL: convert here, into `saved`);
+   *  x_planes_out / e_planes_out caller-owned plane buffers the layer fills next to x_out / edge_out;
+   *  wplanes                     caller-owned buffer (GpsLayerPlan.wplanes_bytes) for the planes of every weight;
+   *                              wplanes_valid != 0: it already holds this layer's current weights (packed once per
+   *                              optimiser step instead of once per forward call). */
+  GpsPlanes x_planes_in, e_planes_in, x_planes_out, e_planes_out;
+  void* wplanes; int64_t wplanes_bytes; int32_t wplanes_valid; int32_t reserved2;
 } GpsLayerArgs;
 
 typedef struct {
@@ -173,6 +198,7 @@ typedef struct {
   int64_t bwd_workspace_bytes;
   int64_t fwd_launches;         /* kernels the forward enqueues  */
   int64_t bwd_launches;         /* kernels the backward enqueues */
+  int64_t wplanes_bytes;        /* ABI 3: size of the optional persistent weight-plane buffer (GpsLayerArgs.wplanes) */
 } GpsLayerPlan;
 
 /* Sizes for the given configuration/graph (only sizes and type fields of args are read). */
