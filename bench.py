@@ -246,6 +246,16 @@ def workload_config(name, spec, local, glob, heads, drop, adrop, n_gpus):
 
 
 # ================================================================================ our arm
+def trace(msg):
+    """GPS_BENCH_TRACE=1: stage markers on stderr (+ a watchdog that dumps every thread's stack if a stage hangs)."""
+    if os.environ.get("GPS_BENCH_TRACE") == "1":
+        import faulthandler
+        faulthandler.cancel_dump_traceback_later()
+        faulthandler.dump_traceback_later(int(os.environ.get("GPS_BENCH_TRACE_TIMEOUT", "120")), exit=True)
+        sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {msg}\n")
+        sys.stderr.flush()
+
+
 def run_ours(args):
     import graphgps_b200
     from graphgps_b200 import _lib
@@ -322,9 +332,11 @@ def run_ours(args):
     # ---------------- device-resident timing
     # Eager warm-up (also sizes the shared workspace), then one CUDA graph per rotating batch: a replay
     # re-executes the captured kernel sequence (forward + backward of the layer) with no host work.
+    trace("eager warm-up")
     for i in range(max(args.warmup, NUM_BATCHES)):
         step(i)
     barrier()
+    trace("capture")
     graphs = None
     graphs_local = None            # the same step without the collectives (N > 1: exposes the all-reduce cost)
     launches_per_step = None
@@ -350,19 +362,19 @@ def run_ours(args):
                 step(i, reduce=True)
         torch.cuda.current_stream().wait_stream(side)
         barrier()
-        if world > 1:
-            try:     # NCCL collectives captured in the same graph as the step
+        if world > 1 and os.environ.get("GPS_BENCH_NCCL_IN_GRAPH") == "1":
+            try:     # NCCL collectives captured in the same graph as the step (measured: ~0.5 ms of host time per launch)
                 graphs = capture_all(True)
                 collective_in_graph = True
             except Exception as e:   # noqa: BLE001
                 sys.stderr.write(f"[bench] capturing the collectives failed ({e!r}); they run after each replay\n")
                 graphs = None
                 torch.cuda.synchronize()
-            graphs_local = capture_all(False)
-            if graphs is None:
-                graphs = graphs_local
-        else:
-            graphs = capture_all(False)
+        # default: the graph holds fwd+bwd and records the gradient-group events as external event nodes; the
+        # collectives are enqueued after each replay and wait on those events (overlap without NCCL graph nodes)
+        graphs_local = capture_all(False)
+        if graphs is None:
+            graphs = graphs_local
 
     def run_step(i):
         if graphs is None:
@@ -372,9 +384,11 @@ def run_ours(args):
             if world > 1 and not collective_in_graph:
                 allreduce_grads()
 
+    trace("graph warm-up")
     for i in range(args.warmup):
         run_step(i)
     barrier()
+    trace("timed region")
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -399,6 +413,7 @@ def run_ours(args):
     ms_total = float(t.item())
 
     # N > 1: the same replays without the collectives -> what the all-reduce still costs after overlap
+    trace("no-collective replays")
     local_ms = None
     if world > 1 and graphs_local is not None:
         for i in range(args.warmup):
@@ -418,6 +433,7 @@ def run_ours(args):
         local_ms = float(tl.item()) / args.steps
 
     # eager (no CUDA graph) number for the same loop, reported alongside
+    trace("eager timing")
     eager_ms = None
     if graphs is not None:
         for i in range(3):
@@ -439,6 +455,7 @@ def run_ours(args):
     # build, layer forward + backward, D2H of x_out and grad_x into pinned host memory.  The copies run on their
     # own streams (PCIe is full duplex), two steps deep, so step k+1's inputs travel while step k computes; the
     # timed region spans the first H2D to the last D2H (device events), i.e. it includes every byte moved.
+    trace("e2e")
     pinned = [b.clone().pin_memory() for b in cpu_batches]
     static = [b.clone().to(dev) for b in cpu_batches]
     host_x = [torch.empty(b.x.shape).pin_memory() for b in cpu_batches]
@@ -523,7 +540,9 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e_ms_total = float(t.item())
 
+    trace("roofline probe")
     roof = roofline_probe(lib, layer, dev_batches[0], spec, heads, args) if rank == 0 else None
+    trace("stack")
 
     # ---------------- the model's layer stack (gps_model.py:100,105-108): L GPSLayers back to back, fwd+bwd, as
     # ONE captured CUDA graph over a resident batch (graph structure shared by all layers).  Measured last and
@@ -535,21 +554,12 @@ def run_ours(args):
             gstack = graphgps_b200.GPSStack(spec.layers, spec.dim, local, glob, heads, dropout=drop, attn_dropout=adrop,
                                             precision=args.precision).to(dev).train()
             sbucket = gstack.make_grad_bucket(overlap=world > 1)
-            coll = (lambda: sbucket.allreduce_overlapped()) if world > 1 else None
-            steps_c = []
-            for i in range(2):
-                b = dev_batches[i]
-                try:
-                    steps_c.append(gstack.capture(b, cts[i][0], cts[i][1] if gated else None, bucket=sbucket,
-                                                  collective=coll))
-                except Exception:   # noqa: BLE001 - collectives not capturable here: stack without them, said so below
-                    if coll is None:
-                        raise
-                    coll = None
-                    torch.cuda.synchronize()
-                    steps_c.append(gstack.capture(b, cts[i][0], cts[i][1] if gated else None, bucket=sbucket))
+            coll = (lambda: sbucket.allreduce_overlapped()) if world > 1 else (lambda: None)
+            steps_c = [gstack.capture(dev_batches[i], cts[i][0], cts[i][1] if gated else None, bucket=sbucket)
+                       for i in range(2)]
             for i in range(4):
                 steps_c[i % 2].replay()
+                coll()
             barrier()
             se = []
             nst = min(args.steps, 50)
@@ -558,6 +568,7 @@ def run_ours(args):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 steps_c[i % 2].replay()
+                coll()
                 e1.record()
                 se.append((e0, e1))
             barrier()
@@ -569,11 +580,12 @@ def run_ours(args):
                      "graphs_per_s": spec.num_graphs * world / (sms * 1e-3),
                      "how": f"graphgps_b200.GPSStack: {spec.layers} GPSLayers fwd+bwd in one captured CUDA graph per rank "
                             f"(shared graph structure, plane hand-off between layers, one gradient bucket"
-                            + (", per-layer all-reduce overlapped with the backward of the layers below" if coll else "")
+                            + (", per-layer all-reduce segments overlapped with the backward of the layers below" if world > 1 else "")
                             + f"), batch resident, L2 flushed between steps, {nst} steps, max over ranks"}
         except Exception as e:   # noqa: BLE001 - the headline numbers above must survive
             stack = {"layers": spec.layers, "measured": False, "error": repr(e)[:300]}
 
+    trace("report")
     if rank == 0:
         B = spec.num_graphs
         value = B * world * args.steps / (ms_total * 1e-3)
@@ -596,8 +608,8 @@ def run_ours(args):
             "gemm_fallbacks": int(lib.gps_fallback_count()),
             "allreduce": (None if world == 1 else {
                 "bytes": int(bucket.flat.numel() * 4), "in_graph": bool(collective_in_graph),
-                "how": "in-place NCCL AVG on the static gradient bucket; early segment (FFN/out-proj/norm gradients) on a "
-                       "communication stream under the rest of the backward pass, late segment at the end",
+                "how": "in-place NCCL AVG on the static gradient bucket, three segments per layer on a communication stream, "
+                       "each released by an event the backward pass records when that gradient group is final",
                 "ms_per_step_without_collectives": local_ms,
                 "exposed_ms_per_step": (None if local_ms is None else ms_total / args.steps - local_ms)}),
             "execution": ("CUDA graph replay (one captured fwd+bwd"
@@ -614,7 +626,14 @@ def run_ours(args):
         }
         print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # destroy_process_group() blocks forever while captured CUDA graphs that contain NCCL kernels are alive
+        # (observed with torch 2.11 / NCCL 2.28): release them, synchronise, and leave without the collective teardown
+        trace("teardown")
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def roofline_probe(lib, layer, b, spec, heads, args):

@@ -68,6 +68,7 @@ class GpsLayerArgs(C.Structure):
         ("ev_grads_early", _fp),
         ("x_planes_in", GpsPlanes), ("e_planes_in", GpsPlanes), ("x_planes_out", GpsPlanes), ("e_planes_out", GpsPlanes),
         ("wplanes", _fp), ("wplanes_bytes", C.c_int64), ("wplanes_valid", C.c_int32), ("reserved2", C.c_int32),
+        ("ev_grads_mid", _fp), ("ev_grads_done", _fp),
     ]
 
 

@@ -136,7 +136,8 @@ struct Side {
 static int opt_flags() {
   static const int v = [] {
     const char* e = getenv("GPS_B200_OPT");
-    return e ? atoi(e) : 7;   // 8 measured slower on B200 (0.573 vs 0.552 ms/step, profiles/r1_ab_switches.txt)
+    return e ? atoi(e) : 7;   // 8 measured slower on B200 (0.478 vs 0.465 ms/step in round 2 as well); 16 (two-part Wcat
+                              // weight gradient) too: 0.476 vs 0.465 on one GPU and no gain at N = 2
   }();
   return v;
 }
@@ -173,8 +174,9 @@ __global__ void k_pack(PackDesc pd, float* __restrict__ Wcat, float* __restrict_
   for (int c = threadIdx.x * 4; c < pd.d; c += blockDim.x * 4) st4(dst + c, ld4(src + c));
   if (threadIdx.x == 0) bcat[r] = pd.seg[s].b ? pd.seg[s].b[r - row0] : 0.f;
 }
-__global__ void k_unpack(PackDesc pd, const float* __restrict__ gWcat, const float* __restrict__ gbcat, int accumulate) {
-  const int r = blockIdx.x;
+__global__ void k_unpack(PackDesc pd, const float* __restrict__ gWcat, const float* __restrict__ gbcat, int accumulate,
+                         int row_begin) {
+  const int r = blockIdx.x + row_begin;
   int row0 = 0, s = 0;
   while (s < pd.nseg - 1 && r >= row0 + pd.seg[s].rows) row0 += pd.seg[s++].rows;
   if (pd.seg[s].gw) {
@@ -956,10 +958,17 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   const bool early_edge = (opt & 4) != 0;
   // data-parallel hook: the caller's event is recorded on the weight-gradient stream once the early gradient group
   // (FFN, attention output projection, norm2 / norm1_local / norm1_attn) has been enqueued there
-  auto early_done = [&]() -> int {
-    if (a->ev_grads_early) GPS_CUDA(cudaEventRecord((cudaEvent_t)a->ev_grads_early, s2));
+  // (recorded as EXTERNAL events under stream capture, so that collectives enqueued outside the captured graph can wait
+  // on them after each replay: NCCL kernels inside a graph cost ~0.5 ms of host time per launch on this stack)
+  auto record_ev = [&](void* ev, cudaStream_t s) -> int {
+    if (!ev) return GPS_OK;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    GPS_CUDA(cudaStreamIsCapturing(s, &cs));
+    GPS_CUDA(cudaEventRecordWithFlags((cudaEvent_t)ev, s, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal
+                                                                                               : cudaEventRecordDefault));
     return GPS_OK;
   };
+  auto early_done = [&]() -> int { return record_ev(a->ev_grads_early, s2); };
   // accumulators of the last two GEMMs of the pass are zeroed now, while their streams are idle, instead of on the tail
   const bool gx_splitk = P.Wy >= 1024 && N > 0 && !((opt & 8) && P.gated && P.attn && sd && P.qkv_off > 0 && P.qkv_off < P.Wy);
   if (P.Wy) {
@@ -983,6 +992,24 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
       GPS_TRY(colsum(P.gY1 + r0, P.Wy, N, rows, P.gbcat + r0, s2));
     }
     return N > 0 ? gemm(w, s2) : GPS_OK;
+  };
+  // The weight gradient of the fused node projection in two parts (GPS_B200_OPT bit 16, default on): rows [0, qkv_off)
+  // (A, B, D, E / GCN lin) as soon as the message-passing backward has produced their gY1 columns - under the attention
+  // backward - and the in_proj rows at the end.  Shortens the tail of the pass and lets a data-parallel caller reduce
+  // the local model's gradients early (ev_grads_mid).
+  const bool wgrad_split = (opt & 16) && sd && !((opt & 8) && P.gated && P.attn) && P.qkv_off > 0 && P.qkv_off < P.Wy && N > 0;
+  auto unpack_rows = [&](int64_t r0, int64_t rows) -> int {
+    PackDesc pdsc = pack_desc(a, P);
+    k_unpack<<<(unsigned)rows, 128, 0, s2>>>(pdsc, P.gWcat, P.gbcat, g_grads_accumulate ? 1 : 0, (int)r0);
+    GPS_LAUNCH_CHECK();
+    return GPS_OK;
+  };
+  auto mid_done = [&]() -> int {   // on s2, after the local model's weight gradients
+    if (wgrad_split) {
+      GPS_TRY(wcat_wgrad(0, P.qkv_off));
+      GPS_TRY(unpack_rows(0, P.qkv_off));
+    }
+    return record_ev(a->ev_grads_mid, s2);
   };
 
   cudaStream_t se = (P.gated && sd && early_edge) ? sd->s4 : st;   // stream of the edge BatchNorm backward
@@ -1165,6 +1192,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     // C: dC = g_e^T e ; g_edge_attr = grad_edge_out + g_e C
     GPS_TRY(wfork(st));
     GPS_TRY(linear_wgrad(P.g_e, d, a->edge_attr, d, E, d, d, a->gcn_C.grad_weight, a->gcn_C.grad_bias, prec, s2, P.ge_p, P.e_p));
+    GPS_TRY(mid_done());
     if (a->grad_edge_attr && E > 0) {
       GemmParams g;
       g.M = (int)E; g.N = (int)d; g.K = (int)d;
@@ -1206,6 +1234,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(wfork(st));
     GPS_TRY(linear_wgrad(g_l1, d, P.h1, d, N, d, d, a->gine_lin1.grad_weight, a->gine_lin1.grad_bias, prec, s2, g_l1_p, P.h1_p));
     GPS_TRY(linear_wgrad(P.g_h1, d, P.agg, d, N, d, d, a->gine_lin0.grad_weight, a->gine_lin0.grad_bias, prec, s2, P.gh1_p, P.agg_p));
+    GPS_TRY(mid_done());
     GemmParams g2;  // g_agg = g_h1 W0
     g2.M = (int)N; g2.N = (int)d; g2.K = (int)d;
     g2.A = P.g_h1; g2.lda = (int)d; g2.B = a->gine_lin0.weight; g2.ldb = (int)d; g2.tb = 1; g2.C = P.g_agg; g2.ldc = (int)d;
@@ -1229,6 +1258,8 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
       GPS_TRY(colsum(g_h, d, N, d, a->gcn_conv.grad_bias, st));
     }
     GPS_TRY(gcn_bwd(a->graph, d, g_h, P.dinv, P.gY1, P.Wy, st, P.gY1_p));
+    GPS_TRY(wfork(st));
+    GPS_TRY(mid_done());
     g_x_local = P.g_xloc;
   }
 
@@ -1239,9 +1270,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     const int64_t wl = P.qkv_off, wg = P.Wy - P.qkv_off;
     GPS_TRY(wfork(st));
     GPS_TRY(wcat_wgrad(wl, wg));
-    PackDesc pdsc = pack_desc(a, P);
-    k_unpack<<<(unsigned)pdsc.total_rows, 128, 0, s2>>>(pdsc, P.gWcat, P.gbcat, g_grads_accumulate ? 1 : 0);
-    GPS_LAUNCH_CHECK();
+    GPS_TRY(unpack_rows(0, P.Wy));
     GemmParams g;   // g_x += g_hA + gY1[:, wl:] Wcat[wl:]  (accumulated onto the first share)
     g.M = (int)N; g.N = (int)d; g.K = (int)wg;
     g.A = P.gY1 + wl; g.lda = (int)P.Wy; g.B = P.Wcat + wl * d; g.ldb = (int)d; g.tb = 1; g.C = a->grad_x; g.ldc = (int)d;
@@ -1255,20 +1284,23 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(gemm(g, st));
   } else if (P.Wy) {
     GPS_TRY(wfork(st));
-    GemmParams w;
-    w.M = (int)P.Wy; w.N = (int)d; w.K = (int)N;
-    w.A = P.gY1; w.lda = (int)P.Wy; w.ta = 1; w.B = a->x; w.ldb = (int)d; w.tb = 1; w.C = P.gWcat; w.ldc = (int)d;
-    w.splitk = splitk_for(N, P.Wy, d) < 2 ? 2 : splitk_for(N, P.Wy, d);
-    w.colsum_a = P.gbcat; w.precision = prec;
-    w.Ap = P.gY1_p; w.Bp = P.x_p;
-    if (prec == GPS_PREC_BF16 && w.Ap.hi && N > 0) {   // exact bias gradients in bf16 mode (see linear_wgrad)
-      w.colsum_a = nullptr;
-      GPS_TRY(colsum(P.gY1, P.Wy, N, P.Wy, P.gbcat, s2));
+    if (wgrad_split) {
+      GPS_TRY(wcat_wgrad(P.qkv_off, P.Wy - P.qkv_off));
+      GPS_TRY(unpack_rows(P.qkv_off, P.Wy - P.qkv_off));
+    } else {
+      GemmParams w;
+      w.M = (int)P.Wy; w.N = (int)d; w.K = (int)N;
+      w.A = P.gY1; w.lda = (int)P.Wy; w.ta = 1; w.B = a->x; w.ldb = (int)d; w.tb = 1; w.C = P.gWcat; w.ldc = (int)d;
+      w.splitk = splitk_for(N, P.Wy, d) < 2 ? 2 : splitk_for(N, P.Wy, d);
+      w.colsum_a = P.gbcat; w.precision = prec;
+      w.Ap = P.gY1_p; w.Bp = P.x_p;
+      if (prec == GPS_PREC_BF16 && w.Ap.hi && N > 0) {   // exact bias gradients in bf16 mode (see linear_wgrad)
+        w.colsum_a = nullptr;
+        GPS_TRY(colsum(P.gY1, P.Wy, N, P.Wy, P.gbcat, s2));
+      }
+      if (N > 0) GPS_TRY(gemm(w, s2));
+      GPS_TRY(unpack_rows(0, P.Wy));
     }
-    if (N > 0) GPS_TRY(gemm(w, s2));
-    PackDesc pdsc = pack_desc(a, P);
-    k_unpack<<<(unsigned)pdsc.total_rows, 128, 0, s2>>>(pdsc, P.gWcat, P.gbcat, g_grads_accumulate ? 1 : 0);
-    GPS_LAUNCH_CHECK();
     GemmParams g;
     g.M = (int)N; g.N = (int)d; g.K = (int)P.Wy;
     g.A = P.gY1; g.lda = (int)P.Wy; g.B = P.Wcat; g.ldb = (int)d; g.tb = 1; g.C = a->grad_x; g.ldc = (int)d;
@@ -1285,6 +1317,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(add3(P.g_xp, d, nullptr, 0, nullptr, 0, a->grad_x, d, N, d, st));   // Performer only
   }
   if (sd) GPS_TRY(sd->join(st));
+  GPS_TRY(record_ev(a->ev_grads_done, st));
   return GPS_OK;
 }
 

@@ -11,18 +11,30 @@ every parameter's `.grad` is a view of it and `gps_layer_backward` adds its grad
 those views (GpsLayerArgs.reserved0 bit 1).  CUDA-graph replays, the optimiser and the collective
 therefore all see the same memory: the all-reduce runs in place on the bucket (ReduceOp.AVG on NCCL,
 no copy-in / scale / copy-out) and can be captured in the same CUDA graph as the step.  Parameters are
-laid out in two contiguous groups per layer - "early" (FFN, attention output projection and the three
-GPSLayer norms, final a few hundred microseconds before the backward pass ends) and "late" (the node/edge
-projections, final only at the very end) - so the early group's collective can be issued on a side stream
-while the rest of the backward pass still runs (`GradBucket.enable_overlap()` / `allreduce_overlapped()`).
+laid out in three contiguous groups per layer in the order the backward pass finishes them - "early" (FFN,
+attention output projection, the three GPSLayer norms), "mid" (the local model: A..E / GINE nn / GCN lin and its
+BatchNorms, minus the rows of the fused node projection) and "late" (the fused node projection A,B,D,E + in_proj /
+to_q,k,v, whose one weight-gradient GEMM is the last kernel of the pass) - and the library records an event per
+group, so each group's collective is issued on a communication stream while the rest of the backward pass
+(and, in a stack, the backward of the layers below) still runs (`enable_overlap()` / `allreduce_overlapped()`).
 """
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
 
+# gradient groups of a GPSLayer in the order the backward pass finishes them (csrc/layer.cu: ev_grads_early / _mid / _done)
 _EARLY_PREFIXES = ("ff_linear1.", "ff_linear2.", "norm2.", "norm1_local.", "norm1_attn.",
                    "self_attn.out_proj.", "self_attn.to_out.")
+_LATE_PREFIXES = ("self_attn.in_proj", "self_attn.to_q.", "self_attn.to_k.", "self_attn.to_v.",
+                  "local_model.A.", "local_model.B.", "local_model.D.", "local_model.E.", "local_model.lin.")   # Wcat rows
+EARLY, MID, LATE = 0, 1, 2
+
+
+def _group(name):
+    if name.startswith(_EARLY_PREFIXES):
+        return EARLY
+    return LATE if name.startswith(_LATE_PREFIXES) else MID
 
 
 def shard_graph_range(num_graphs: int, rank: int, world: int):
@@ -41,17 +53,17 @@ class GradBucket:
 
     def __init__(self, layers, device=None):
         self.layers = list(layers)
-        entries = []   # (layer index, early?, name, param)
+        entries = []   # (layer index, group, name, param)
         for li, layer in enumerate(self.layers):
             for n, p in layer.named_parameters():
-                entries.append((li, n.startswith(_EARLY_PREFIXES), n, p))
+                entries.append((li, _group(n), n, p))
         if not entries:
             raise ValueError("GradBucket: no parameters")
         device = device or entries[0][3].device
-        # layer-major; inside a layer the early group first.  16-float alignment keeps every view 64-byte aligned.
-        order = sorted(range(len(entries)), key=lambda i: (entries[i][0], not entries[i][1]))
+        # layer-major; inside a layer early, mid, late.  16-float alignment keeps every view 64-byte aligned.
+        order = sorted(range(len(entries)), key=lambda i: (entries[i][0], entries[i][1]))
         offs, off = {}, 0
-        self.segments = []   # (layer, early, begin, end) in element offsets
+        self.segments = []   # (layer, group, begin, end) in element offsets
         cur = None
         for i in order:
             li, early, n, p = entries[i]
@@ -77,37 +89,46 @@ class GradBucket:
         return self
 
     def enable_overlap(self):
-        """Give every layer an event that gps_layer_backward records when its early gradient group is final, and a
-        communication stream on which `allreduce_overlapped` runs the collectives."""
+        """Give every layer the three events gps_layer_backward records as its gradient groups become final (early:
+        FFN / out-proj / GPSLayer norms; mid: local model; done: everything incl. in_proj) and a communication stream on
+        which `allreduce_overlapped` runs the collectives."""
         dev = self.flat.device
         self.comm_stream = torch.cuda.Stream(device=dev)
         self.events = []
         for layer in self.layers:
-            ev = torch.cuda.Event()
-            ev.record(torch.cuda.current_stream(dev))     # materialise the cudaEvent_t handle
-            layer.__dict__["grad_early_event"] = ev
-            self.events.append(ev)
+            evs = tuple(torch.cuda.Event() for _ in range(3))
+            for ev in evs:
+                ev.record(torch.cuda.current_stream(dev))     # materialise the cudaEvent_t handles
+            layer.__dict__["grad_events"] = evs
+            self.events.append(evs)
         return self
 
     def allreduce_overlapped(self, group=None):
-        """Call right after backward() has been enqueued (layers ran last-to-first).  Per layer, the early segment is
-        reduced as soon as its event fires - under the rest of that layer's backward pass and under the backward of the
-        layers below it - and the late segment when the whole pass is done; the caller's stream waits for both.
-        Capturable into the same CUDA graph as the step."""
+        """Call right after backward() has been enqueued (layers ran last-to-first).  Every segment is reduced as soon as
+        its event fires: under the rest of that layer's backward pass and under the backward of the layers below it.
+        Only the last-finished segment (layer 0's fused-projection gradients, 7d^2 floats) is exposed; the caller's stream
+        waits for the communication stream at the end.  Works after a CUDA-graph replay of the step as well: the library
+        records the events as external event nodes under capture, so the collectives stay outside the graph (NCCL kernels
+        captured inside a graph cost ~0.5 ms of host time per launch with torch 2.11 / NCCL 2.28)."""
         cur = torch.cuda.current_stream(self.flat.device)
         cs = self.comm_stream
         with torch.cuda.stream(cs):
             for li in reversed(range(len(self.layers))):
-                cs.wait_event(self.events[li])
-                self.allreduce(group, segments=[self.segment(li, True)])
-            cs.wait_stream(cur)
-            late = [self.segment(li, False) for li in reversed(range(len(self.layers)))]
-            self.allreduce(group, segments=[t for t in late if t is not None])
+                for grp in (EARLY, MID, LATE):
+                    seg = self.segment(li, grp)
+                    if seg is None:
+                        continue
+                    cs.wait_event(self.events[li][grp])
+                    self.allreduce(group, segments=[seg])
         cur.wait_stream(cs)
 
-    def segment(self, layer: int, early: bool):
-        for li, e, b, en in self.segments:
-            if li == layer and e == early:
+    def segment(self, layer: int, grp):
+        grp = {True: EARLY, False: None}.get(grp, grp) if isinstance(grp, bool) else grp
+        if grp is None:   # legacy "not early": everything after the early group of this layer
+            parts = [(b, en) for li, g, b, en in self.segments if li == layer and g != EARLY]
+            return self.flat[min(b for b, _ in parts):max(e for _, e in parts)] if parts else None
+        for li, g, b, en in self.segments:
+            if li == layer and g == grp:
                 return self.flat[b:en]
         return None
 

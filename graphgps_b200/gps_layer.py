@@ -239,9 +239,9 @@ class _GPSLayerFn(torch.autograd.Function):
         if ctx.hand is not None:
             args.x_planes_in, args.e_planes_in, args.wplanes, args.wplanes_bytes = ctx.hand[:4]
             args.wplanes_valid = 1
-        ev = layer.__dict__.get("grad_early_event")
-        if ev is not None:
-            args.ev_grads_early = ev.cuda_event
+        evs = layer.__dict__.get("grad_events")
+        if evs is not None:
+            args.ev_grads_early, args.ev_grads_mid, args.ev_grads_done = (e.cuda_event for e in evs)
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.gps_layer_backward(C.byref(args), stream), "gps_layer_backward")
         # (ctx.saved_buf stays alive with the autograd node: backward(retain_graph=True) may run again)

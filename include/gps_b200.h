@@ -190,6 +190,13 @@ typedef struct {
    *                              optimiser step instead of once per forward call). */
   GpsPlanes x_planes_in, e_planes_in, x_planes_out, e_planes_out;
   void* wplanes; int64_t wplanes_bytes; int32_t wplanes_valid; int32_t reserved2;
+
+  /* ABI 3 (backward, optional): two more cudaEvent_t of the same kind as ev_grads_early.  ev_grads_mid: the local
+   * model's gradients (A, B, C, D, E / GINE nn / GCN lin, bn_node_x, bn_edge_e) are final - the weight gradient of the
+   * fused node projection is computed in two parts for this, the local column block as soon as the message-passing
+   * backward is done, the in_proj block at the end.  ev_grads_done: every gradient of this layer is final. */
+  void* ev_grads_mid;
+  void* ev_grads_done;
 } GpsLayerArgs;
 
 typedef struct {
