@@ -98,6 +98,8 @@ SYMBOLS = {
                                         _f32, _u64, _u64, _fp]),
     "gps_attention_backward": (C.c_int, [C.POINTER(GpsGraph), _i64, _i64, _fp, _fp, _fp, _i64, _fp, _fp, _i64,
                                          _fp, _fp, _fp, _fp, _fp, _i64, _f32, _u64, _u64, _fp]),
+    "gps_attention_forward_tc": (C.c_int, [C.POINTER(GpsGraph), _i64, _i64, _fp, _fp, _i64, _fp, _i64, _fp, _f32, _u64, _u64,
+                                           _i32, _fp]),
     "gps_dropout_mask": (C.c_int, [_fp, _i64, _i64, _f32, _u64, _u64, _i32, _fp]),
     "gps_to_planes": (C.c_int, [_fp, _i64, _i64, _i64, _fp, _fp, _i64, _fp]),
     "gps_gemm_planes": (C.c_int, [_fp, _fp, _i64, _i32, _fp, _fp, _i64, _i32, _fp, _i64, _fp, _fp, _i64, _i64, _i64, _i64,
@@ -107,6 +109,7 @@ SYMBOLS = {
     "gps_launch_count": (C.c_ulonglong, []),
     "gps_debug_set": (None, [C.c_int]),
     "gps_debug_tma": (None, [C.c_int, _fp]),
+    "gps_debug_attn": (None, [_fp]),
 }
 
 _lib = None

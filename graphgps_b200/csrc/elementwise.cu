@@ -39,9 +39,9 @@ static int row_geom(int64_t rows, int64_t d, int nstat, RowGeom* g) {
   return GPS_OK;
 }
 
+// body of one row-wise stage run by blocks [0, vgrid) (virtual block index vb: two stages can share one launch)
 template <class Op>
-__global__ void __launch_bounds__(1024) k_rowwise(Op op, int64_t rows) {
-  extern __shared__ float4 sm[];
+__device__ __forceinline__ void rowwise_body(Op& op, int64_t rows, int vb, int vgrid, float4* sm) {
   const int c4 = threadIdx.x, ry = threadIdx.y, RY = blockDim.y, C4 = blockDim.x;
   constexpr int NS = Op::NS;
   float4 acc[NS > 0 ? NS : 1];
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(1024) k_rowwise(Op op, int64_t rows) {
   for (int s = 0; s < (NS > 0 ? NS : 1); ++s) acc[s] = f4zero();
   op.prepare(c4);
 #pragma unroll 4
-  for (int64_t r = (int64_t)blockIdx.x * RY + ry; r < rows; r += (int64_t)gridDim.x * RY) op.row(r, c4, acc);
+  for (int64_t r = (int64_t)vb * RY + ry; r < rows; r += (int64_t)vgrid * RY) op.row(r, c4, acc);
   if (NS > 0) {
     if (RY > 1) {
 #pragma unroll
@@ -77,9 +77,28 @@ __global__ void __launch_bounds__(1024) k_rowwise(Op op, int64_t rows) {
   op.finish(c4, ry);
 }
 
+template <class Op>
+__global__ void __launch_bounds__(1024) k_rowwise(Op op, int64_t rows) {
+  extern __shared__ float4 sm[];
+  rowwise_body(op, rows, (int)blockIdx.x, (int)gridDim.x, sm);
+}
+
+// two independent row-wise stages in one launch: blocks [0, ga) run `a`, the rest run `b` (same block shape)
+template <class OpA, class OpB>
+__global__ void __launch_bounds__(1024) k_rowwise2(OpA a, int64_t rowsA, int ga, OpB b, int64_t rowsB) {
+  extern __shared__ float4 sm[];
+  if ((int)blockIdx.x < ga) {
+    a.vb = (int)blockIdx.x;
+    rowwise_body(a, rowsA, (int)blockIdx.x, ga, sm);
+  } else {
+    b.vb = (int)blockIdx.x - ga;
+    rowwise_body(b, rowsB, (int)blockIdx.x - ga, (int)gridDim.x - ga, sm);
+  }
+}
+
 struct BnRegs {  // per-thread column constants: y = z * sc + sh ; zhat = (z - mean) * invstd
   float4 mean, invstd, gamma, beta;
-  __device__ void load(const BnView& v, int c4) {
+  __device__ void load(const BnView& v, int c4, int vb = -1) {
     gamma = ld4(v.gamma + c4 * 4);
     beta = ld4(v.beta + c4 * 4);
     if (v.mode == 0) {
@@ -102,7 +121,7 @@ struct BnRegs {  // per-thread column constants: y = z * sc + sh ; zhat = (z - m
       }
       mean = make_float4(m[0], m[1], m[2], m[3]);
       invstd = make_float4(is[0], is[1], is[2], is[3]);
-      if (blockIdx.x == 0 && threadIdx.y == 0) {   // one CTA publishes the statistics and the running update
+      if ((vb < 0 ? (int)blockIdx.x : vb) == 0 && threadIdx.y == 0) {   // one CTA publishes the statistics and the running update
         st4(v.save_mean + c4 * 4, mean);
         st4(v.save_invstd + c4 * 4, invstd);
         if (v.running_mean) {
@@ -146,8 +165,9 @@ struct OpBnActRes {
   const float* R; float* out; int64_t d;
   BnView bn; int act; DropCfg drop; double* stats; Planes outp;
   BnRegs reg;
+  int vb = -1;   // virtual block index when two stages share a launch (k_rowwise2)
   __device__ void prepare(int c4) {
-    reg.load(bn, c4);
+    reg.load(bn, c4, vb);
     if (drop.p > 0.f && drop.offset_dev) drop.offset += *drop.offset_dev;
   }
   __device__ void row(int64_t r, int c4, float4* acc) {
@@ -308,6 +328,26 @@ int bn_act_residual(const float* z, int64_t ldz, const float* R, float* out, int
   }
   OpBnActRes<false> op{z, ldz, R, out, d, bn, act, drop, nullptr, outp};
   return launch_rowwise(op, rows, d, stream);
+}
+
+// both GatedGCN outputs in one launch: x_loc = x + drop(act(BN_x(x~))) with column sums, e_out = e + drop(act(BN_e(e^)))
+int bn_act_residual2(const float* zx, const float* Rx, float* outx, int64_t N, BnView bnx, DropCfg dropx, double* statsx,
+                     const float* ze, const float* Re, float* oute, int64_t E, BnView bne, DropCfg drope, Planes outep,
+                     int64_t d, int act, cudaStream_t stream) {
+  if (N == 0 || E == 0 || !statsx) {   // degenerate sizes / eval mode: two plain launches
+    GPS_TRY(bn_act_residual(zx, d, Rx, outx, N, d, bnx, act, dropx, statsx, stream));
+    return bn_act_residual(ze, d, Re, oute, E, d, bne, act, drope, nullptr, stream, outep);
+  }
+  RowGeom g;
+  GPS_TRY(row_geom(N, d, 2, &g));                    // the statistics stage fixes the (fat) block shape
+  const int RY = (int)g.block.y;
+  int64_t gb = ceil_div(E, (int64_t)RY * 4);
+  if (gb > kNumSMs * 2) gb = kNumSMs * 2;
+  OpBnActRes<true> opx{zx, d, Rx, outx, d, bnx, act, dropx, statsx, Planes()};
+  OpBnActRes<false> ope{ze, d, Re, oute, d, bne, act, drope, nullptr, outep};
+  k_rowwise2<<<dim3((unsigned)(g.grid.x + gb)), g.block, g.smem, stream>>>(opx, N, (int)g.grid.x, ope, E);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
 }
 
 int bn_combine(const float* a, BnView bna, const float* b, BnView bnb, float* out, int64_t rows, int64_t d,

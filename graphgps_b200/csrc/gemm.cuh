@@ -1,5 +1,7 @@
 // gemm.cuh — parameter block shared by the dense-product kernels (gemm_simt.cu, gemm_tc.cu).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace gps {
@@ -40,6 +42,9 @@ struct GemmParams {
   // are given the TMA-fed kernel (gemm_tma.cu) runs and A/B (fp32) are not read.  Cp: optional plane copy of the
   // result for the next GEMM; C may then be null (planes-only output).
   Planes Ap, Bp, Cp;
+  // Cp column remap for the attention operands: output column c lands at (c / cp_hd) * cp_hd_pad + c % cp_hd and the
+  // cp_hd_pad - cp_hd pad columns of every head are written as zeros (per-head layout padded to a multiple of 16)
+  int cp_hd = 0, cp_hd_pad = 0, cp_col0 = 0;   // cp_col0: first output column of the remapped block
 };
 
 struct ToPlanesItem { const float* src; int64_t ld; int rows; int cols; Planes dst; };
@@ -47,6 +52,9 @@ struct ToPlanesItem { const float* src; int64_t ld; int rows; int cols; Planes d
 int to_planes(const ToPlanesItem* items, int n, cudaStream_t stream);
 // TMA-fed tcgen05 product on plane operands; GPS_ERR_UNSUPPORTED when the planes are missing / misaligned
 int gemm_tma(const GemmParams& p, cudaStream_t stream);
+// rank-3 tensor map {cols, rows, planes} over a plane pair with a {64, box_rows, 1} SWIZZLE_128B box (cached)
+int make_tensor_map(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int planes, int64_t rows, int64_t cols, int64_t ld,
+                    int box_rows, CUtensorMap* out);
 void gemm_tma_set_force_bn(int bn);
 void gemm_tma_set_trace(unsigned long long* buf);   // bring-up: per-CTA phase timestamps (tools/gemm_trace.py)
 

@@ -300,8 +300,15 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const float4 bb = p.bias ? ld4(p.bias + col) : f4zero();
         const float* mk = p.mask_src ? p.mask_src + row0 * p.ldmask + col : nullptr;
         const int64_t mk_st = (int64_t)rpp * p.ldmask;
-        __nv_bfloat16* ph = p.Cp.hi ? p.Cp.hi + row0 * p.Cp.ld + col : nullptr;
-        __nv_bfloat16* pl = p.Cp.lo ? p.Cp.lo + row0 * p.Cp.ld + col : nullptr;
+        // plane column: identity, or the per-head padded layout of the attention operands (cp_hd)
+        int pcol = col, npad = 0;
+        if (p.cp_hd > 0) {
+          const int cl = col - (p.cp_col0), hq = cl / p.cp_hd, cw = cl - hq * p.cp_hd;
+          pcol = hq * p.cp_hd_pad + cw;
+          npad = (cw + 4 == p.cp_hd) ? p.cp_hd_pad - p.cp_hd : 0;   // this thread also zeroes the head's pad columns
+        }
+        __nv_bfloat16* ph = p.Cp.hi ? p.Cp.hi + row0 * p.Cp.ld + pcol : nullptr;
+        __nv_bfloat16* pl = p.Cp.lo ? p.Cp.lo + row0 * p.Cp.ld + pcol : nullptr;
         const int64_t p_st = (int64_t)rpp * p.Cp.ld;
         const bool relu = p.act == GPS_ACT_RELU;
         if (fast) {
@@ -346,6 +353,10 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                   *reinterpret_cast<uint2*>(pl + (k + u) * p_st) =
                       make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
                 }
+                for (int z = 0; z < npad; z += 4) {
+                  *reinterpret_cast<uint2*>(ph + (k + u) * p_st + 4 + z) = make_uint2(0u, 0u);
+                  if (pl) *reinterpret_cast<uint2*>(pl + (k + u) * p_st + 4 + z) = make_uint2(0u, 0u);
+                }
               }
               s1 = f4add(s1, w[u]);
               s2 = f4fma(w[u], w[u], s2);
@@ -373,7 +384,10 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             if (r1) w = f4add(w, ld4(r1 + k * r1_st));
             if (r2) w = f4add(w, ld4(r2 + k * r2_st));
             if (cp) st4(cp + k * c_st, w);
-            if (ph) planes_store4(p.Cp, row, col, w);
+            if (ph) {
+              planes_store4(p.Cp, row, pcol, w);
+              for (int z = 0; z < npad; z += 4) planes_store4(p.Cp, row, pcol + 4 + z, f4zero());
+            }
             s1 = f4add(s1, w);
             s2 = f4fma(w, w, s2);
           }
@@ -480,6 +494,15 @@ int tensor_map(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int planes, int
   *out = m;
   return GPS_OK;
 }
+
+}  // namespace
+
+int make_tensor_map(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int planes, int64_t rows, int64_t cols, int64_t ld,
+                    int box_rows, CUtensorMap* out) {
+  return tensor_map(hi, lo, planes, rows, cols, ld, box_rows, out);
+}
+
+namespace {
 
 inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 

@@ -38,6 +38,9 @@ struct DropCfg {
 // out = R + dropout(act(BN(z)))  [+ column sums of out into stats]   (gatedgcn_layer.py:72-83)
 int bn_act_residual(const float* z, int64_t ldz, const float* R, float* out, int64_t rows, int64_t d,
                     BnView bn, int act, DropCfg drop, double* stats, cudaStream_t stream, Planes outp = Planes());
+int bn_act_residual2(const float* zx, const float* Rx, float* outx, int64_t N, BnView bnx, DropCfg dropx, double* statsx,
+                     const float* ze, const float* Re, float* oute, int64_t E, BnView bne, DropCfg drope, Planes outep,
+                     int64_t d, int act, cudaStream_t stream);
 // out = BN_a(a) [+ BN_b(b)]   (gps_layer.py:194,217,222 and :229)
 int bn_combine(const float* a, BnView bna, const float* b, BnView bnb, float* out, int64_t rows, int64_t d,
                cudaStream_t stream, Planes outp = Planes());
@@ -97,5 +100,14 @@ int attention_bwd(const GpsGraph& g, int64_t heads, int64_t hd, const float* Q, 
                   float* dQ, float* dK, float* dV, int64_t ldg, float p_drop, uint64_t seed, uint64_t offset,
                   cudaStream_t stream, const unsigned long long* offset_dev = nullptr, Planes dQp = Planes(),
                   Planes dKp = Planes(), Planes dVp = Planes());
+
+// tcgen05 version (attention_tc.cu): Q, K, V from bf16 hi/lo planes in the per-head padded layout
+// column (which * H + h) * hd_pad + k, hd_pad = attention_tc_hd_pad(hd), pad columns zero
+void attention_tc_set_debug(float* buf);   // bring-up: 3 x 128 x 128 floats (S, P, raw O of CTA (0,0))
+bool attention_tc_supported(int64_t hd);
+int64_t attention_tc_hd_pad(int64_t hd);
+int attention_tc_fwd(const GpsGraph& g, int64_t heads, int64_t hd, Planes qkv, float* O, int64_t ldo, Planes Op, float* lse,
+                     float p_drop, uint64_t seed, uint64_t offset, const unsigned long long* offset_dev, int precision,
+                     cudaStream_t stream);
 
 }  // namespace gps

@@ -213,6 +213,8 @@ struct Plan {
   bool use_planes;
   Planes x_p, e_p, O_p, s_p, hid_p, agg_p, h1_p, Wcat_p, C_p, out_p, ff1_p, ff2_p, g0_p, g1_p, pq_p, pk_p, pv_p;
   Planes gt_p, ghid_p, ghA_p, ge_p, gY1_p, gtmp_p, gtmp2_p, gtmp3_p, gl1_p, gh1_p;
+  Planes qkv_p;        // Q | K | V per head, padded to hd_pad columns: operands of the tcgen05 attention
+  bool attn_tc;        // softmax attention on the tensor cores (attention_tc.cu)
   int64_t saved_bytes;
   int64_t wplanes_bytes;
   // forward workspace
@@ -233,6 +235,19 @@ static bool planes_enabled() {
     return !(e && (strcmp(e, "tc") == 0 || strcmp(e, "simt") == 0));
   }();
   return v;
+}
+
+// Forward softmax attention on the tensor cores (attention_tc.cu) when the batch's graphs are large enough for 128 x 128
+// tiles to pay: measured on B200 (round 2) the tcgen05 kernel needs 57 us at the PCQM4M shape (mean 14 nodes per graph:
+// a 128-row tile sees ~45 useful keys of 256, one latency-bound wave of 116 CTAs) against 25 us for the CUDA-core kernel,
+// and wins once a graph fills a tile (ogbg-code2 shape, mean 125 / max ~1000 nodes).  GPS_B200_ATTN=simt | tc overrides.
+static bool attn_tc_enabled(int64_t N, int64_t B) {
+  static const int mode = [] {
+    const char* e = getenv("GPS_B200_ATTN");
+    return e && strcmp(e, "simt") == 0 ? 0 : (e && strcmp(e, "tc") == 0 ? 2 : 1);
+  }();
+  if (mode != 1) return mode == 2;
+  return B > 0 && N >= 64 * B;
 }
 
 static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
@@ -342,6 +357,8 @@ static int make_plan(const GpsLayerArgs* a, Plan* P, bool bind) {
     P->x_p = x_in ? handed(a->x_planes_in) : mkplanes(S, N, d);
     if (P->gated || P->gine) P->e_p = e_in ? handed(a->e_planes_in) : mkplanes(S, E, d);
     if (P->attn || P->perf) P->O_p = mkplanes(S, N, kout);
+    P->attn_tc = P->attn && attention_tc_supported(P->hd) && attn_tc_enabled(N, a->graph.B);
+    if (P->attn_tc) P->qkv_p = mkplanes(S, N, 3 * P->H * attention_tc_hd_pad(P->hd));
     P->s_p = mkplanes(S, N, d);
     P->hid_p = mkplanes(S, N, 2 * d);
     if (P->gine) {
@@ -772,6 +789,9 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
       g.bias = P.bcat + wl; g.precision = a->precision;
       set_bpk(g, P.pk_cat, P.Wy, d, wl);
       g.Ap = P.x_p; g.Bp = P.Wcat_p.rows(wl);
+      if (P.attn_tc) {   // Q | K | V additionally as padded per-head operand planes for the tcgen05 attention
+        g.Cp = P.qkv_p; g.cp_hd = (int)P.hd; g.cp_hd_pad = (int)attention_tc_hd_pad(P.hd); g.cp_col0 = 0;
+      }
       GPS_TRY(gemm(g, sg));
     }
     if (wl > 0) {
@@ -793,10 +813,9 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
     GPS_TRY(gatedgcn_fwd(a->graph, d, P.Y1, P.Y1 + d, P.Y1 + 2 * d, P.Y1 + 3 * d, P.Wy, P.ehat, P.xt,
                          stats(BN_X), stats(BN_E), st));
     // x_loc = x + drop(act(BN(x~)));  e_out = e + drop(act(BN(e^)))   (gatedgcn_layer.py:72-83)
-    GPS_TRY(bn_act_residual(P.xt, d, a->x, P.xloc, N, d, bn_view_fwd(P, a, BN_X, a->bn_node_x, N), act, drop(GPS_SITE_GCN_X),
-                            stats(BN_L), st));
-    GPS_TRY(bn_act_residual(P.ehat, d, a->edge_attr, a->edge_out, E, d, bn_view_fwd(P, a, BN_E, a->bn_edge_e, E), act,
-                            drop(GPS_SITE_GCN_E), nullptr, st, out_planes(a->e_planes_out)));
+    GPS_TRY(bn_act_residual2(P.xt, a->x, P.xloc, N, bn_view_fwd(P, a, BN_X, a->bn_node_x, N), drop(GPS_SITE_GCN_X), stats(BN_L),
+                             P.ehat, a->edge_attr, a->edge_out, E, bn_view_fwd(P, a, BN_E, a->bn_edge_e, E),
+                             drop(GPS_SITE_GCN_E), out_planes(a->e_planes_out), d, act, st));
   } else if (P.gine) {
     GPS_TRY(gine_fwd(a->graph, d, a->x, a->edge_attr, a->gine_eps, P.agg, st, P.agg_p));
     GemmParams g;  // h1 = act(agg W0^T + b0)
@@ -825,8 +844,12 @@ static int layer_forward(const GpsLayerArgs* a, cudaStream_t st) {
   // ---- global attention  (gps_layer.py:198-218, 234-241)
   if (P.attn) {
     const float* Q = P.Y1 + P.qkv_off;
-    GPS_TRY(attention_fwd(a->graph, P.H, P.hd, Q, Q + d, Q + 2 * d, P.Wy, P.O, d, P.lse, pa, a->seed, a->offset, sg,
-                          (const unsigned long long*)a->offset_dev, P.O_p));
+    if (P.attn_tc)
+      GPS_TRY(attention_tc_fwd(a->graph, P.H, P.hd, P.qkv_p, P.O, d, P.O_p, P.lse, pa, a->seed, a->offset,
+                               (const unsigned long long*)a->offset_dev, a->precision, sg));
+    else
+      GPS_TRY(attention_fwd(a->graph, P.H, P.hd, Q, Q + d, Q + 2 * d, P.Wy, P.O, d, P.lse, pa, a->seed, a->offset, sg,
+                            (const unsigned long long*)a->offset_dev, P.O_p));
     GemmParams g;  // hA = x + drop(O Wo^T + bo)
     g.M = (int)N; g.N = (int)d; g.K = (int)d;
     g.A = P.O; g.lda = (int)d; g.B = a->attn_out.weight; g.ldb = (int)d; g.C = P.hA; g.ldc = (int)d;
@@ -1396,6 +1419,7 @@ extern "C" void gps_debug_tma(int force_bn, void* trace) {
   gemm_tma_set_force_bn(force_bn);
   gemm_tma_set_trace((unsigned long long*)trace);
 }
+extern "C" void gps_debug_attn(void* buf) { attention_tc_set_debug((float*)buf); }
 
 extern "C" int gps_layer_plan(const GpsLayerArgs* args, GpsLayerPlan* plan) {
   GPS_REQUIRE(args && plan, GPS_ERR_ARG, "gps_layer_plan: null argument");
@@ -1464,6 +1488,15 @@ extern "C" int gps_attention_forward(const GpsGraph* g, int64_t heads, int64_t h
                                      uint64_t seed, uint64_t offset, void* stream) {
   GPS_REQUIRE(g && Q && K && V && O && lse, GPS_ERR_ARG, "attention_forward: null argument");
   return attention_fwd(*g, heads, hd, Q, K, V, ld, O, ldo, lse, p_drop, seed, offset, (cudaStream_t)stream);
+}
+
+extern "C" int gps_attention_forward_tc(const GpsGraph* g, int64_t heads, int64_t hd, const void* qkv_hi, const void* qkv_lo,
+                                        int64_t ld, float* O, int64_t ldo, float* lse, float p_drop, uint64_t seed,
+                                        uint64_t offset, int32_t precision, void* stream) {
+  GPS_REQUIRE(g && qkv_hi && O && lse, GPS_ERR_ARG, "attention_forward_tc: null argument");
+  Planes q{(__nv_bfloat16*)qkv_hi, (__nv_bfloat16*)qkv_lo, ld};
+  return attention_tc_fwd(*g, heads, hd, q, O, ldo, Planes(), lse, p_drop, seed, offset, nullptr, precision,
+                          (cudaStream_t)stream);
 }
 
 extern "C" int gps_attention_backward(const GpsGraph* g, int64_t heads, int64_t hd, const float* Q, const float* K,

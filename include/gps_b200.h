@@ -57,6 +57,9 @@ void gps_debug_set(int v);
 /* bring-up hook of the TMA-fed GEMM (tools/gemm_trace.py): force_bn = forced tile width (0 = heuristic); trace = device
  * buffer of 256 x 16 uint64 that the first 256 CTAs of each launch fill with globaltimer phase stamps (NULL = off) */
 void gps_debug_tma(int force_bn, void* trace);
+/* bring-up hook of the tcgen05 attention: device buffer of 3 x 128 x 128 floats that CTA (0,0) fills with its first
+ * S tile, P tile and raw O accumulator (NULL = off) */
+void gps_debug_attn(void* buf);
 
 /* ------------------------------------------------------------------------------------------
  * Graph structure of one mini-batch (constant across the L layers and across fwd/bwd).
@@ -252,6 +255,13 @@ int gps_gine_aggregate_forward(const GpsGraph* g, int64_t d, const float* x, con
 int gps_attention_forward(const GpsGraph* g, int64_t heads, int64_t hd, const float* Q,
                           const float* K, const float* V, int64_t ld, float* O, int64_t ldo,
                           float* lse, float p_drop, uint64_t seed, uint64_t offset, void* stream);
+/* ABI 3: the same forward on the tensor cores (csrc/attention_tc.cu: tcgen05 S = QK^T and O += PV, TMA-staged tiles,
+ * block-diagonal graph mask applied in-kernel).  qkv_hi/qkv_lo: bf16 hi/lo planes [N, ld] holding Q | K | V per head in
+ * the padded layout column (which * heads + h) * hd_pad + k with hd_pad = round_up(hd, 16) and zero pad columns
+ * (qkv_lo NULL for GPS_PREC_BF16).  Same O / lse conventions as gps_attention_forward, so either backward applies. */
+int gps_attention_forward_tc(const GpsGraph* g, int64_t heads, int64_t hd, const void* qkv_hi, const void* qkv_lo,
+                             int64_t ld, float* O, int64_t ldo, float* lse, float p_drop, uint64_t seed,
+                             uint64_t offset, int32_t precision, void* stream);
 /* (the layer-level calls additionally honour GpsLayerArgs.offset_dev) */
 int gps_attention_backward(const GpsGraph* g, int64_t heads, int64_t hd, const float* Q,
                            const float* K, const float* V, int64_t ld, const float* O,
