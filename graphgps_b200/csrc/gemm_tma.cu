@@ -259,7 +259,7 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     const int rip = tid / G, cg = tid - rip * G;
     const int col = n0 + cg * 4;
     const bool col_ok = rip < rpp && col < p.N;
-    float4 s1 = f4zero(), s2 = f4zero();
+    float4 s1 = f4zero(), s2 = f4zero(), q0 = f4zero(), q1 = f4zero();   // sum w, sum w^2, sum w*zhat_0, sum w*zhat_1
     if (col_ok) {
       // rows of this thread: r = rip + k * rpp, k < nrows.  Everything is addressed through per-thread base pointers
       // advanced by a constant stride, and the loop is unrolled by 4 rows so that the shared/global loads of a group are
@@ -311,6 +311,13 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         __nv_bfloat16* pl = p.Cp.lo ? p.Cp.lo + row0 * p.Cp.ld + pcol : nullptr;
         const int64_t p_st = (int64_t)rpp * p.Cp.ld;
         const bool relu = p.act == GPS_ACT_RELU;
+        // fused BatchNorm-backward reductions (bnred): per-column constants -mean and invstd, row pointers into z_k
+        const float* bz0 = p.bnred[0].sums ? p.bnred[0].z + row0 * p.bnred[0].ldz + col : nullptr;
+        const float* bz1 = p.bnred[1].sums ? p.bnred[1].z + row0 * p.bnred[1].ldz + col : nullptr;
+        const int64_t bz0_st = (int64_t)rpp * p.bnred[0].ldz, bz1_st = (int64_t)rpp * p.bnred[1].ldz;
+        float4 bm0 = f4zero(), bi0 = f4zero(), bm1 = f4zero(), bi1 = f4zero();
+        if (bz0) { bm0 = f4scale(ld4(p.bnred[0].mean + col), -1.f); bi0 = ld4(p.bnred[0].invstd + col); }
+        if (bz1) { bm1 = f4scale(ld4(p.bnred[1].mean + col), -1.f); bi1 = ld4(p.bnred[1].invstd + col); }
         if (fast) {
           for (int k = 0; k < nrows; k += 4) {
             float4 w[4];
@@ -360,6 +367,8 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
               }
               s1 = f4add(s1, w[u]);
               s2 = f4fma(w[u], w[u], s2);
+              if (bz0) q0 = f4fma(w[u], f4mul(f4add(ld4(bz0 + (k + u) * bz0_st), bm0), bi0), q0);
+              if (bz1) q1 = f4fma(w[u], f4mul(f4add(ld4(bz1 + (k + u) * bz1_st), bm1), bi1), q1);
             }
           }
         } else {
@@ -394,25 +403,40 @@ k_gemm_tma(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         }
       }
     }
-    if (p.stats) {
-      // column sums: the rpp threads that share a column group meet in shared memory, one double atomic per column per CTA
-      float4* rs = reinterpret_cast<float4*>(red);
+    if (p.stats || p.bnred[0].sums || p.bnred[1].sums) {
+      // column sums: the rpp threads that share a column group meet in shared memory (the staging tile is free again
+      // after the barrier), one double atomic per column per CTA and accumulator
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float4* rs = reinterpret_cast<float4*>(stage);
       if (rip < rpp) {
-        rs[(rip * G + cg) * 2] = s1;
-        rs[(rip * G + cg) * 2 + 1] = s2;
+        rs[(rip * G + cg) * 4] = s1;
+        rs[(rip * G + cg) * 4 + 1] = s2;
+        rs[(rip * G + cg) * 4 + 2] = q0;
+        rs[(rip * G + cg) * 4 + 3] = q1;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (tid < G && n0 + tid * 4 < p.N) {
-        float4 t1 = f4zero(), t2 = f4zero();
-        for (int y = 0; y < rpp; ++y) {
-          t1 = f4add(t1, rs[(y * G + tid) * 2]);
-          t2 = f4add(t2, rs[(y * G + tid) * 2 + 1]);
-        }
+        float4 t[4] = {f4zero(), f4zero(), f4zero(), f4zero()};
+        for (int y = 0; y < rpp; ++y)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) t[k] = f4add(t[k], rs[(y * G + tid) * 4 + k]);
         const int c0 = n0 + tid * 4;
-        atomic_add_f64(&p.stats[c0 + 0], (double)t1.x); atomic_add_f64(&p.stats[c0 + 1], (double)t1.y);
-        atomic_add_f64(&p.stats[c0 + 2], (double)t1.z); atomic_add_f64(&p.stats[c0 + 3], (double)t1.w);
-        atomic_add_f64(&p.stats[(int64_t)p.N + c0 + 0], (double)t2.x); atomic_add_f64(&p.stats[(int64_t)p.N + c0 + 1], (double)t2.y);
-        atomic_add_f64(&p.stats[(int64_t)p.N + c0 + 2], (double)t2.z); atomic_add_f64(&p.stats[(int64_t)p.N + c0 + 3], (double)t2.w);
+        auto add4 = [&](double* dst, float4 v) {
+          atomic_add_f64(dst + 0, (double)v.x); atomic_add_f64(dst + 1, (double)v.y);
+          atomic_add_f64(dst + 2, (double)v.z); atomic_add_f64(dst + 3, (double)v.w);
+        };
+        if (p.stats) {
+          add4(p.stats + c0, t[0]);
+          add4(p.stats + (int64_t)p.N + c0, t[1]);
+        }
+        if (p.bnred[0].sums) {
+          add4(p.bnred[0].sums + c0, t[0]);
+          add4(p.bnred[0].sums + (int64_t)p.N + c0, t[2]);
+        }
+        if (p.bnred[1].sums) {
+          add4(p.bnred[1].sums + c0, t[0]);
+          add4(p.bnred[1].sums + (int64_t)p.N + c0, t[3]);
+        }
       }
     }
   }
@@ -550,6 +574,12 @@ int gemm_tma(const GemmParams& p, cudaStream_t stream) {
   }
   if (p.colsum_a && !p.ta) {
     set_error("gemm: colsum_a needs ta == 1");
+    return GPS_ERR_ARG;
+  }
+  if ((p.bnred[0].sums || p.bnred[1].sums) &&
+      (p.splitk > 1 || p.C_pre || (p.mask_src && !p.mask_is_post) || p.p_drop != 0.f || p.p_drop2 != 0.f ||
+       (p.act >= 0 && p.act != GPS_ACT_RELU))) {
+    set_error("gemm: fused BatchNorm-backward reductions need the plain epilogue (no split-K / dropout / GELU)");
     return GPS_ERR_ARG;
   }
   const int mt = (int)ceil_div(p.M, BM);

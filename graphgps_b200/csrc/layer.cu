@@ -76,6 +76,8 @@ int gemm(const GemmParams& p, cudaStream_t stream) {
     if (rc != GPS_ERR_UNSUPPORTED) return rc;
   }
   GPS_REQUIRE(p.A && p.B && p.C, GPS_ERR_UNSUPPORTED, "gemm: plane operands rejected and no fp32 operands to fall back to");
+  GPS_REQUIRE(!p.bnred[0].sums && !p.bnred[1].sums, GPS_ERR_UNSUPPORTED,
+              "gemm: fused BatchNorm-backward reductions exist in the TMA kernel only");
   GemmParams q = p;
   if (q.Cp.hi) {   // the fp32 kernels do not write planes: convert afterwards
     q.Cp = Planes();
@@ -136,7 +138,8 @@ struct Side {
 static int opt_flags() {
   static const int v = [] {
     const char* e = getenv("GPS_B200_OPT");
-    return e ? atoi(e) : 7;   // 8 measured slower on B200 (0.478 vs 0.465 ms/step in round 2 as well); 16 (two-part Wcat
+    return e ? atoi(e) : 103; // 32: norm1_local apply + bn_node_x reduce in one pass; 64: norm1_local / norm1_attn reduces
+                              // in the epilogue of the GEMM that produces g_s; 8 measured slower on B200 (0.478 vs 0.465 ms/step in round 2 as well); 16 (two-part Wcat
                               // weight gradient) too: 0.476 vs 0.465 on one GPU and no gain at N = 2
   }();
   return v;
@@ -1071,6 +1074,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   GPS_TRY(bn_bwd_apply(a->grad_x_out, d, P.t, d, N, d, v2, -1, nodrop, sums(BN_2), P.g_t, d, a->norm2.grad_weight,
                        a->norm2.grad_bias, st, g_grads_accumulate, P.gt_p));
 
+  bool fused_la = false;
   // ---- FFN (gps_layer.py:253-257)
   const float* g_ff2 = P.g_t;  // gradient at the output of ff_linear2 (after ff_dropout2)
   Planes g_ff2_p = P.gt_p;
@@ -1099,16 +1103,38 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g2.R1 = P.g_t; g2.ldr1 = (int)d; g2.precision = prec;
     set_bpt(g2, P.pt_ff1, d, 2 * d);
     g2.Ap = P.ghid_p; g2.Bp = P.ff1_p;
+    // norm1_local and norm1_attn both take g_s as their upstream gradient (gps_layer.py:194,217,222): their backward
+    // reductions ride this GEMM's epilogue instead of two more passes over g_s (GPS_B200_OPT bit 64)
+    fused_la = (opt & 64) && P.use_planes && g2.Ap.hi && g2.Bp.hi && N > 0;
+    if (fused_la) {
+      if (P.gated || P.gine || P.gcn) {
+        BnView v = bn_view(P, BN_L, a->norm1_local);
+        g2.bnred[0].z = P.xloc; g2.bnred[0].ldz = (int)d; g2.bnred[0].mean = v.mean; g2.bnred[0].invstd = v.invstd;
+        g2.bnred[0].sums = sums(BN_L);
+      }
+      if (P.attn || P.perf) {
+        BnView v = bn_view(P, BN_A, a->norm1_attn);
+        g2.bnred[1].z = P.hA; g2.bnred[1].ldz = (int)d; g2.bnred[1].mean = v.mean; g2.bnred[1].invstd = v.invstd;
+        g2.bnred[1].sums = sums(BN_A);
+      }
+    }
     GPS_TRY(gemm(g2, st));
   }
 
   const bool loc = P.gated || P.gine || P.gcn;
+  bool chain_x = false;
   // ---- norm1_local / norm1_attn (gps_layer.py:194,217): g_xloc, g_hA
   if (loc) {
     BnView v = bn_view(P, BN_L, a->norm1_local);
-    GPS_TRY(bn_bwd_reduce(P.g_s, d, P.xloc, d, N, d, v, -1, nodrop, sums(BN_L), st));
-    GPS_TRY(bn_bwd_apply(P.g_s, d, P.xloc, d, N, d, v, -1, nodrop, sums(BN_L), P.g_xloc, d,
-                         a->norm1_local.grad_weight, a->norm1_local.grad_bias, st, g_grads_accumulate, P.gl1_p));
+    if (!fused_la) GPS_TRY(bn_bwd_reduce(P.g_s, d, P.xloc, d, N, d, v, -1, nodrop, sums(BN_L), st));
+    chain_x = P.gated && N > 0 && (opt & 32);
+    if (chain_x)   // ... and the reduction of local_model.bn_node_x's backward in the same pass (one launch less)
+      GPS_TRY(bn_bwd_apply_chain(P.g_s, d, P.xloc, d, N, d, v, sums(BN_L), P.g_xloc, d, a->norm1_local.grad_weight,
+                                 a->norm1_local.grad_bias, g_grads_accumulate, P.gl1_p, P.xt, d,
+                                 bn_view(P, BN_X, a->bn_node_x), act, drop(GPS_SITE_GCN_X), sums(BN_X), st));
+    else
+      GPS_TRY(bn_bwd_apply(P.g_s, d, P.xloc, d, N, d, v, -1, nodrop, sums(BN_L), P.g_xloc, d,
+                           a->norm1_local.grad_weight, a->norm1_local.grad_bias, st, g_grads_accumulate, P.gl1_p));
   }
   if (!P.attn && !P.perf) {   // no global model: the early group ends with norm1_local's gradients (stream st)
     GPS_TRY(wfork(st));
@@ -1117,7 +1143,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   if (two_branches && sd) GPS_TRY(sd->order(st, sa));   // attention-branch backward runs next to the local-model backward
   if (P.attn) {
     BnView v = bn_view(P, BN_A, a->norm1_attn);
-    GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), sa));
+    if (!fused_la) GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), sa));
     GPS_TRY(bn_bwd_apply(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), P.g_hA, d, a->norm1_attn.grad_weight,
                          a->norm1_attn.grad_bias, sa, g_grads_accumulate, P.ghA_p));
     // hA = x + drop(O Wo^T + bo)
@@ -1148,7 +1174,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   if (P.perf) {
     const int64_t inner = P.inner, NH = N * P.H, dh = a->perf_dim_head;
     BnView v = bn_view(P, BN_A, a->norm1_attn);
-    GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), sa));
+    if (!fused_la) GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), sa));
     GPS_TRY(bn_bwd_apply(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), P.g_hA, d, a->norm1_attn.grad_weight,
                          a->norm1_attn.grad_bias, sa, g_grads_accumulate));
     const float* g_ao = P.g_hA;   // hA = x + drop_pd(drop_pa(to_out(O)))
@@ -1202,7 +1228,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   if (P.gated) {
     // x_loc = x + drop(act(BN_x(x~))): g_x~ -> gY1[:, 0:d]  (gatedgcn_layer.py:72-83)
     BnView vx = bn_view(P, BN_X, a->bn_node_x);
-    GPS_TRY(bn_bwd_reduce(P.g_xloc, d, P.xt, d, N, d, vx, act, drop(GPS_SITE_GCN_X), sums(BN_X), st));
+    if (!chain_x) GPS_TRY(bn_bwd_reduce(P.g_xloc, d, P.xt, d, N, d, vx, act, drop(GPS_SITE_GCN_X), sums(BN_X), st));
     GPS_TRY(bn_bwd_apply(P.g_xloc, d, P.xt, d, N, d, vx, act, drop(GPS_SITE_GCN_X), sums(BN_X), P.gY1, P.Wy,
                          a->bn_node_x.grad_weight, a->bn_node_x.grad_bias, st, g_grads_accumulate, P.gY1_p));
     if (!early_edge) GPS_TRY(edge_bn_bwd());
