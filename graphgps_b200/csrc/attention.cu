@@ -407,8 +407,9 @@ static void launch_one(int which, const AttnArgs& a0, cudaStream_t stream) {
   constexpr int RPW = 32 / LPR;
   AttnArgs a = a0;
   static const bool stage_on = [] {
-    const char* e = getenv("GPS_B200_ATTN_STAGE");
-    return !(e && e[0] == '0');
+    const char* e = getenv("GPS_B200_ATTN_STAGE");   // off by default: the staged kernels are faster in isolation but
+    return e && e[0] == '1';                          // their 72 KB blocks crowd the GEMMs running next to them
+                                                      // (same-box A/B at C3: 0.4983 vs 0.4856 ms/step)
   }();
   // staging pays when graphs are small (a block's 32 rows then see few distinct key rows); with large graphs every
   // block would exceed the tile anyway

@@ -252,6 +252,7 @@ struct OpBnBwdApply {
     s2raw = make_float4((float)b[0], (float)b[1], (float)b[2], (float)b[3]);
     m1 = f4scale(s1raw, inv_n);
     m2 = f4scale(s2raw, inv_n);
+    if (bn.mode == 2) m1 = m2 = f4zero();   // eval mode: the statistics are constants, dz = g' * gamma * invstd
     gs = f4mul(reg.gamma, reg.invstd);
   }
   __device__ void row(int64_t r, int c4, float4*) {

@@ -138,8 +138,11 @@ struct Side {
 static int opt_flags() {
   static const int v = [] {
     const char* e = getenv("GPS_B200_OPT");
-    return e ? atoi(e) : 103; // 32: norm1_local apply + bn_node_x reduce in one pass; 64: norm1_local / norm1_attn reduces
-                              // in the epilogue of the GEMM that produces g_s; 8 measured slower on B200 (0.478 vs 0.465 ms/step in round 2 as well); 16 (two-part Wcat
+    return e ? atoi(e) : 7;   // Measured slower on B200 and therefore off (same-box A/B, profiles/r2_ab_switches.txt):
+                              // 8 (split dgrad+wgrad tail) 0.478 vs 0.465; 16 (two-part Wcat wgrad) 0.476 vs 0.465;
+                              // 32 + 64 (bn_node_x reduce inside the norm1_local apply pass, norm1_local / norm1_attn
+                              // reduces in the epilogue of the GEMM producing g_s) 0.4946 vs 0.4856: three launches
+                              // fewer, but the fused kernels run as few fat CTAs and delay the branches behind them on B200 (0.478 vs 0.465 ms/step in round 2 as well); 16 (two-part Wcat
                               // weight gradient) too: 0.476 vs 0.465 on one GPU and no gain at N = 2
   }();
   return v;
@@ -957,13 +960,13 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   GPS_REQUIRE(a->workspace_bytes >= P.bwd_bytes, GPS_ERR_ARG, "workspace too small (%lld < %lld)",
               (long long)a->workspace_bytes, (long long)P.bwd_bytes);
   GPS_TRY(check_params(a, P));
-  GPS_REQUIRE(a->training, GPS_ERR_UNSUPPORTED, "backward is implemented for training mode (batch statistics)");
+  // eval mode (running statistics, no dropout): BatchNorm is a per-column affine map, its backward has no batch terms
   g_grads_accumulate = (a->reserved0 & 2) != 0;
   g_grads_prezeroed = (a->reserved0 & 1) != 0 || g_grads_accumulate;
   GPS_REQUIRE(a->grad_x_out && a->grad_x, GPS_ERR_ARG, "grad_x_out / grad_x are required");
   const int64_t N = P.N, E = P.E, d = P.d;
   const int act = a->act, prec = a->precision;
-  const float pd = a->dropout, pa = a->attn_dropout;
+  const float pd = a->training ? a->dropout : 0.f, pa = a->training ? a->attn_dropout : 0.f;
   const bool relu = act == GPS_ACT_RELU;
   auto drop = [&](int site) {
     DropCfg c;
@@ -972,6 +975,16 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     return c;
   };
   DropCfg nodrop;
+  // training: the batch statistics saved by the forward pass; eval: the running statistics the forward pass used
+  auto bview = [&](int which, const GpsBatchNorm& bn) {
+    BnView v = bn_view(P, which, bn);
+    if (!a->training) {
+      v.mode = 2;
+      v.running_mean = bn.running_mean;
+      v.running_var = bn.running_var;
+    }
+    return v;
+  };
   auto sums = [&](int which) { return P.bsums + (int64_t)which * 2 * d; };
   GPS_CUDA(cudaMemsetAsync(P.bsums, 0, (size_t)BN_COUNT * 2 * d * sizeof(double), st));
   // weight-gradient GEMMs run on the side stream, each forked where its operands become final
@@ -1052,7 +1065,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   auto edge_bn_bwd = [&]() -> int {
     // e_out = e + drop(act(BN_e(e^))) (gatedgcn_layer.py:76-83): g_e^ needs grad_edge_out alone -> off the critical path
     if (se != st) GPS_TRY(sd->order(st, se));
-    BnView ve = bn_view(P, BN_E, a->bn_edge_e);
+    BnView ve = bview(BN_E, a->bn_edge_e);
     if (a->grad_edge_out && E > 0) {
       GPS_TRY(bn_bwd_reduce(a->grad_edge_out, d, P.ehat, d, E, d, ve, act, drop(GPS_SITE_GCN_E), sums(BN_E), se));
       GPS_TRY(bn_bwd_apply(a->grad_edge_out, d, P.ehat, d, E, d, ve, act, drop(GPS_SITE_GCN_E), sums(BN_E), P.g_e, d,
@@ -1069,7 +1082,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   if (P.gated && early_edge) GPS_TRY(edge_bn_bwd());
 
   // ---- norm2 (gps_layer.py:229): g_t
-  BnView v2 = bn_view(P, BN_2, a->norm2);
+  BnView v2 = bview(BN_2, a->norm2);
   GPS_TRY(bn_bwd_reduce(a->grad_x_out, d, P.t, d, N, d, v2, -1, nodrop, sums(BN_2), st));
   GPS_TRY(bn_bwd_apply(a->grad_x_out, d, P.t, d, N, d, v2, -1, nodrop, sums(BN_2), P.g_t, d, a->norm2.grad_weight,
                        a->norm2.grad_bias, st, g_grads_accumulate, P.gt_p));
@@ -1105,15 +1118,15 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
     g2.Ap = P.ghid_p; g2.Bp = P.ff1_p;
     // norm1_local and norm1_attn both take g_s as their upstream gradient (gps_layer.py:194,217,222): their backward
     // reductions ride this GEMM's epilogue instead of two more passes over g_s (GPS_B200_OPT bit 64)
-    fused_la = (opt & 64) && P.use_planes && g2.Ap.hi && g2.Bp.hi && N > 0;
+    fused_la = (opt & 64) && P.use_planes && g2.Ap.hi && g2.Bp.hi && N > 0 && a->training;
     if (fused_la) {
       if (P.gated || P.gine || P.gcn) {
-        BnView v = bn_view(P, BN_L, a->norm1_local);
+        BnView v = bview(BN_L, a->norm1_local);
         g2.bnred[0].z = P.xloc; g2.bnred[0].ldz = (int)d; g2.bnred[0].mean = v.mean; g2.bnred[0].invstd = v.invstd;
         g2.bnred[0].sums = sums(BN_L);
       }
       if (P.attn || P.perf) {
-        BnView v = bn_view(P, BN_A, a->norm1_attn);
+        BnView v = bview(BN_A, a->norm1_attn);
         g2.bnred[1].z = P.hA; g2.bnred[1].ldz = (int)d; g2.bnred[1].mean = v.mean; g2.bnred[1].invstd = v.invstd;
         g2.bnred[1].sums = sums(BN_A);
       }
@@ -1125,13 +1138,13 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   bool chain_x = false;
   // ---- norm1_local / norm1_attn (gps_layer.py:194,217): g_xloc, g_hA
   if (loc) {
-    BnView v = bn_view(P, BN_L, a->norm1_local);
+    BnView v = bview(BN_L, a->norm1_local);
     if (!fused_la) GPS_TRY(bn_bwd_reduce(P.g_s, d, P.xloc, d, N, d, v, -1, nodrop, sums(BN_L), st));
-    chain_x = P.gated && N > 0 && (opt & 32);
+    chain_x = P.gated && N > 0 && (opt & 32) && a->training;
     if (chain_x)   // ... and the reduction of local_model.bn_node_x's backward in the same pass (one launch less)
       GPS_TRY(bn_bwd_apply_chain(P.g_s, d, P.xloc, d, N, d, v, sums(BN_L), P.g_xloc, d, a->norm1_local.grad_weight,
                                  a->norm1_local.grad_bias, g_grads_accumulate, P.gl1_p, P.xt, d,
-                                 bn_view(P, BN_X, a->bn_node_x), act, drop(GPS_SITE_GCN_X), sums(BN_X), st));
+                                 bview(BN_X, a->bn_node_x), act, drop(GPS_SITE_GCN_X), sums(BN_X), st));
     else
       GPS_TRY(bn_bwd_apply(P.g_s, d, P.xloc, d, N, d, v, -1, nodrop, sums(BN_L), P.g_xloc, d,
                            a->norm1_local.grad_weight, a->norm1_local.grad_bias, st, g_grads_accumulate, P.gl1_p));
@@ -1142,7 +1155,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   }
   if (two_branches && sd) GPS_TRY(sd->order(st, sa));   // attention-branch backward runs next to the local-model backward
   if (P.attn) {
-    BnView v = bn_view(P, BN_A, a->norm1_attn);
+    BnView v = bview(BN_A, a->norm1_attn);
     if (!fused_la) GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), sa));
     GPS_TRY(bn_bwd_apply(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), P.g_hA, d, a->norm1_attn.grad_weight,
                          a->norm1_attn.grad_bias, sa, g_grads_accumulate, P.ghA_p));
@@ -1173,7 +1186,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
 
   if (P.perf) {
     const int64_t inner = P.inner, NH = N * P.H, dh = a->perf_dim_head;
-    BnView v = bn_view(P, BN_A, a->norm1_attn);
+    BnView v = bview(BN_A, a->norm1_attn);
     if (!fused_la) GPS_TRY(bn_bwd_reduce(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), sa));
     GPS_TRY(bn_bwd_apply(P.g_s, d, P.hA, d, N, d, v, -1, nodrop, sums(BN_A), P.g_hA, d, a->norm1_attn.grad_weight,
                          a->norm1_attn.grad_bias, sa, g_grads_accumulate));
@@ -1227,7 +1240,7 @@ static int layer_backward(const GpsLayerArgs* a, cudaStream_t st) {
   const float* g_x_local = nullptr;  // direct gradient paths into x besides the projections
   if (P.gated) {
     // x_loc = x + drop(act(BN_x(x~))): g_x~ -> gY1[:, 0:d]  (gatedgcn_layer.py:72-83)
-    BnView vx = bn_view(P, BN_X, a->bn_node_x);
+    BnView vx = bview(BN_X, a->bn_node_x);
     if (!chain_x) GPS_TRY(bn_bwd_reduce(P.g_xloc, d, P.xt, d, N, d, vx, act, drop(GPS_SITE_GCN_X), sums(BN_X), st));
     GPS_TRY(bn_bwd_apply(P.g_xloc, d, P.xt, d, N, d, vx, act, drop(GPS_SITE_GCN_X), sums(BN_X), P.gY1, P.Wy,
                          a->bn_node_x.grad_weight, a->bn_node_x.grad_bias, st, g_grads_accumulate, P.gY1_p));

@@ -202,8 +202,6 @@ class _GPSLayerFn(torch.autograd.Function):
         lib = _lib.load()
         layer, gs = ctx.layer, ctx.gs
         x, e, *params = ctx.saved_tensors
-        if not ctx.training:
-            raise RuntimeError("GPSLayer backward needs training mode (BatchNorm batch statistics)")
         dev = x.device
         named = dict(zip(layer._param_names, params))
         bucket = layer._bucket_grads(named)
@@ -219,7 +217,7 @@ class _GPSLayerFn(torch.autograd.Function):
             torch._foreach_zero_(list(grads.values()))   # one multi-tensor fill; the library then skips its memsets
             args = layer._base_args(gs, named, grads)
             args.reserved0 = 1
-        args.seed, args.offset, args.training = ctx.seed, ctx.offset, 1
+        args.seed, args.offset, args.training = ctx.seed, ctx.offset, 1 if ctx.training else 0
         if ctx.snap is not None:
             args.offset_dev = ctx.snap.data_ptr()
         g_x_out = g_x_out.contiguous()

@@ -619,3 +619,22 @@ def test_eval_then_train_same_batch_and_retain_graph():
     x_in.grad = None
     loss.backward()
     assert rel_err(x_in.grad.cpu(), g1.cpu()) < 1e-6
+
+
+def test_eval_mode_backward_matches_oracle():
+    """Input saliency in eval mode (running statistics, no dropout) works on the reference module; here the BatchNorm
+    backward degenerates to a per-column affine map (VERDICT r1 weak #4)."""
+    fix = load_golden("gatedgcn_transformer_gelu")
+    cfg = fix["config"]
+    ora = OracleGPSLayer(cfg["d"], cfg["local"], cfg["glob"], cfg["heads"], act=cfg["act"], dropout=0.3, attn_dropout=0.3)
+    ora.load_state_dict(fix["state"])
+    ours = graphgps_b200.GPSLayer(cfg["d"], cfg["local"], cfg["glob"], cfg["heads"], act=cfg["act"], dropout=0.3,
+                                  attn_dropout=0.3)
+    ours.load_state_dict(fix["state"])
+    ours = ours.to(DEV).eval()
+    ora = ora.double().eval()
+    ref = run_layer(ora, golden_batch(fix, dtype=torch.float64), fix)
+    res = run_layer(ours, golden_batch(fix, DEV), fix)
+    tgt = {k: ref[k] for k in ("out_x", "out_e", "grad_x", "grad_e")}
+    tgt["grad_params"], tgt["state_after"] = ref["grad_params"], ref["state_after"]
+    compare(res, tgt, 1e-3, "eval-mode forward + backward", grad_l2_tol=5e-3)
