@@ -135,3 +135,46 @@ def test_graph_cache_round_trips_on_storage_backed_batches():
     sb = StoreBacked()
     G._cache_put(sb, gs)
     assert G._CACHE_ATTR not in sb.__dict__ and G._cache_get(sb) is gs
+
+
+def test_collate_matches_pyg_conventions():
+    """graphgps_b200.loader.collate: node-offset edge indices, sorted batch vector, ptr offsets (what the layer needs
+    from a PyG Batch), including an empty graph and a graph without edges."""
+    import torch
+    from graphgps_b200.loader import collate
+    g = torch.Generator().manual_seed(0)
+    graphs = [(torch.randn(3, 4, generator=g), torch.tensor([[0, 1, 2], [1, 2, 0]]), torch.randn(3, 4, generator=g)),
+              (torch.zeros(0, 4), torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0, 4)),
+              (torch.randn(2, 4, generator=g), torch.zeros(2, 0, dtype=torch.int64), torch.zeros(0, 4)),
+              (torch.randn(4, 4, generator=g), torch.tensor([[3, 0], [0, 3]]), torch.randn(2, 4, generator=g))]
+    b = collate(graphs)
+    assert b.num_graphs == 4 and b.ptr.tolist() == [0, 3, 3, 5, 9]
+    assert b.batch.tolist() == [0, 0, 0, 2, 2, 3, 3, 3, 3]
+    assert b.edge_index.tolist() == [[0, 1, 2, 8, 5], [1, 2, 0, 5, 8]]
+    assert b.x.shape == (9, 4) and b.edge_attr.shape == (5, 4)
+
+
+def test_stack_and_bucket_structure_on_cpu():
+    """GPSStack mirrors GPSModel's `layers` Sequential (same per-layer state_dict keys); GradBucket groups a GPSLayer's
+    parameters early / mid / late in the order the backward pass finishes them and aliases every .grad to one buffer."""
+    import torch
+    import graphgps_b200
+    from graphgps_b200.dp import EARLY, LATE, MID, GradBucket, _group
+    st = graphgps_b200.GPSStack(2, 16, "CustomGatedGCN", "Transformer", 2)
+    keys = list(st.state_dict().keys())
+    assert "layers.0.local_model.A.weight" in keys and "layers.1.self_attn.in_proj_weight" in keys
+    assert _group("ff_linear1.weight") == EARLY and _group("norm1_attn.bias") == EARLY
+    assert _group("local_model.C.weight") == MID and _group("local_model.bn_edge_e.bias") == MID
+    assert _group("local_model.A.weight") == LATE and _group("self_attn.in_proj_bias") == LATE
+    bucket = GradBucket(list(st.layers))
+    lo, n = bucket.flat.data_ptr(), bucket.flat.numel()
+    total = 0
+    for p in st.parameters():
+        assert lo <= p.grad.data_ptr() < lo + 4 * n and p.grad.shape == p.shape
+        total += p.numel()
+    assert n >= total
+    segs = [(li, g) for li, g, _, _ in bucket.segments]
+    assert segs == [(0, EARLY), (0, MID), (0, LATE), (1, EARLY), (1, MID), (1, LATE)]
+    p = st.layers[1].ff_linear2.weight
+    p.grad.fill_(2.0)
+    assert float(bucket.segment(1, EARLY).sum()) >= 2.0 * p.numel()

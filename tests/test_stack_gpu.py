@@ -95,3 +95,22 @@ def test_stack_captured_step_matches_eager_with_bucket():
     eager2 = _run_keep(stack, b2, ct_x, ct_e)
     torch.cuda.synchronize()
     assert rel_err(step.x_out.cpu(), eager2[0].cpu()) < 1e-6
+
+
+def test_batch_prefetcher_feeds_the_layer_without_changing_results():
+    """SURVEY 8 f4: pinned host batches copied on their own stream `depth` steps ahead, graph structure built on arrival;
+    the layer's outputs must equal the plain `.to(device)` path and every batch must arrive with its structure cached."""
+    from graphgps_b200.loader import BatchPrefetcher
+    torch.manual_seed(3)
+    layer = graphgps_b200.GPSLayer(64, "CustomGatedGCN", "Transformer", 4).to(DEV).eval()
+    host = [make_batch("zinc-gatedgcn", seed=20 + i, dim=64, num_graphs=8 + i) for i in range(5)]
+    with torch.no_grad():
+        ref = [layer(b.clone().to(DEV)).x.clone() for b in host]
+        got = []
+        for b in BatchPrefetcher(host, DEV, depth=2):
+            assert "_gps_b200_graph" in b.__dict__ and b.x.is_cuda
+            got.append(layer(b).x.clone())
+    torch.cuda.synchronize()
+    assert len(got) == len(ref)
+    for a, r in zip(got, ref):
+        assert rel_err(a.cpu(), r.cpu()) < 1e-6
