@@ -103,7 +103,11 @@ class BatchPrefetcher:
                 queue.append(self._issue(nxt))
             cur = torch.cuda.current_stream(self.device)
             cur.wait_event(ev)
-            for t in (b.x, b.edge_index, b.edge_attr, b.batch):
+            held = [b.x, b.edge_index, b.edge_attr, b.batch]
+            gs = b.__dict__.get("_gps_b200_graph")
+            if gs is not None:
+                held += [gs.storage, gs.edge_index, gs.batch]
+            for t in held:
                 if t is not None:
                     t.record_stream(cur)          # allocated on the copy stream, consumed on the compute stream
             yield b
