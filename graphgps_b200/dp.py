@@ -88,6 +88,18 @@ class GradBucket:
         self.flat.zero_()
         return self
 
+    def check_attached(self):
+        """Raises if some parameter's .grad is no longer a view of this bucket (e.g. after
+        `optimizer.zero_grad(set_to_none=True)`): a collective on the bucket would then reduce stale memory."""
+        lo = self.flat.data_ptr()
+        hi = lo + self.flat.numel() * 4
+        for li, layer in enumerate(self.layers):
+            for n, p in layer.named_parameters():
+                g = p.grad
+                if g is None or not (lo <= g.data_ptr() < hi):
+                    raise RuntimeError(f"GradBucket: .grad of layer {li} parameter '{n}' is not a view of the bucket any "
+                                       "more; zero gradients with bucket.zero_() / zero_grad(set_to_none=False)")
+
     def enable_overlap(self):
         """Give every layer the three events gps_layer_backward records as its gradient groups become final (early:
         FFN / out-proj / GPSLayer norms; mid: local model; done: everything incl. in_proj) and a communication stream on
@@ -110,6 +122,7 @@ class GradBucket:
         waits for the communication stream at the end.  Works after a CUDA-graph replay of the step as well: the library
         records the events as external event nodes under capture, so the collectives stay outside the graph (NCCL kernels
         captured inside a graph cost ~0.5 ms of host time per launch with torch 2.11 / NCCL 2.28)."""
+        self.check_attached()
         cur = torch.cuda.current_stream(self.flat.device)
         cs = self.comm_stream
         with torch.cuda.stream(cs):
@@ -137,6 +150,8 @@ class GradBucket:
         world = dist.get_world_size(group)
         if world == 1:
             return
+        if segments is None:
+            self.check_attached()
         parts = segments if segments is not None else [self.flat]
         avg = dist.get_backend(group) == "nccl"
         for t in parts:

@@ -178,3 +178,8 @@ def test_stack_and_bucket_structure_on_cpu():
     p = st.layers[1].ff_linear2.weight
     p.grad.fill_(2.0)
     assert float(bucket.segment(1, EARLY).sum()) >= 2.0 * p.numel()
+    bucket.check_attached()
+    p.grad = None                     # what optimizer.zero_grad(set_to_none=True) does
+    import pytest
+    with pytest.raises(RuntimeError, match="not a view of the bucket"):
+        bucket.check_attached()
