@@ -141,7 +141,7 @@ def test_replay_then_allreduce_equals_mean_of_oracle_grads_2gpu(tmp_path):
     for p in procs:
         p.start()
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=300)
     alive = [p for p in procs if p.is_alive()]
     for p in alive:
         p.kill()
