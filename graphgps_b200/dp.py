@@ -79,6 +79,7 @@ class GradBucket:
             if p.dtype != torch.float32 or p.device != self.flat.device:
                 raise TypeError(f"GradBucket: parameter {n} must be float32 on {self.flat.device}")
             p.grad = self.flat[offs[i]:offs[i] + p.numel()].view_as(p)
+        self._params = [(li, n, p) for li, _, n, p in entries]
         lo = self.flat.data_ptr()
         hi = lo + self.flat.numel() * 4
         for layer in self.layers:
@@ -93,12 +94,11 @@ class GradBucket:
         `optimizer.zero_grad(set_to_none=True)`): a collective on the bucket would then reduce stale memory."""
         lo = self.flat.data_ptr()
         hi = lo + self.flat.numel() * 4
-        for li, layer in enumerate(self.layers):
-            for n, p in layer.named_parameters():
-                g = p.grad
-                if g is None or not (lo <= g.data_ptr() < hi):
-                    raise RuntimeError(f"GradBucket: .grad of layer {li} parameter '{n}' is not a view of the bucket any "
-                                       "more; zero gradients with bucket.zero_() / zero_grad(set_to_none=False)")
+        for li, n, p in self._params:
+            g = p.grad
+            if g is None or not (lo <= g.data_ptr() < hi):
+                raise RuntimeError(f"GradBucket: .grad of layer {li} parameter '{n}' is not a view of the bucket any "
+                                   "more; zero gradients with bucket.zero_() / zero_grad(set_to_none=False)")
 
     def enable_overlap(self):
         """Give every layer the three events gps_layer_backward records as its gradient groups become final (early:
